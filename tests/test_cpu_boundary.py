@@ -1,0 +1,110 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, its parameter inventory
+matches the reference's state_dict (via the golden key lists), host logic of the diffusion mirrors the oracle."""
+import ctypes as C
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from resshift_b200 import _lib
+from resshift_b200.config import preset
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "resshift_b200.h").read_text()
+    declared = set(re.findall(r"\b(rs_[a-z0-9_]+)\s*\(", header))
+    declared -= {"rs_unet_config"}
+    assert declared == set(_lib.declared_symbols())
+    for name in declared:
+        assert hasattr(_lib.lib, name), name
+    assert _lib.lib.rs_version() >= 100
+
+
+@pytest.mark.parametrize("name", ["realsr", "faceir", "inpaint"])
+def test_engine_inventory_matches_reference_state_dict(golden_dir, name):
+    gold = json.loads((golden_dir / f"unet_keys_{name}.json").read_text())
+    ucfg, _ = preset(name)
+    h = C.c_void_p()
+    cfgc = _lib.make_config(ucfg)
+    _lib.check(_lib.lib.rs_unet_create(C.byref(cfgc), C.byref(h)))
+    try:
+        n = _lib.lib.rs_unet_param_count(h)
+        buf = C.create_string_buffer(256)
+        shape = (C.c_int32 * 4)()
+        nd, isb = C.c_int32(), C.c_int32()
+        mine = []
+        for i in range(n):
+            _lib.check(_lib.lib.rs_unet_param_info(h, i, buf, 256, shape, C.byref(nd), C.byref(isb)))
+            mine.append((buf.value.decode(), [shape[j] for j in range(nd.value)]))
+        assert sorted(mine) == sorted((k, s) for k, s, _ in gold["entries"])
+        assert _lib.lib.rs_unet_arena_bytes(h) > 2 * 0.95 * gold["n_params"]     # ~fp16 per parameter
+    finally:
+        _lib.lib.rs_unet_destroy(h)
+
+
+def test_error_reporting_is_by_code_and_message():
+    ucfg, _ = preset("tiny")
+    cfgc = _lib.make_config(ucfg)
+    cfgc.swin_heads = 5                      # head_dim != 32 -> rejected
+    h = C.c_void_p()
+    rc = _lib.lib.rs_unet_create(C.byref(cfgc), C.byref(h))
+    assert rc < 0 and b"head_dim" in _lib.lib.rs_last_error()
+    with pytest.raises(_lib.RsError):
+        _lib.check(rc)
+
+
+def test_module_state_dict_loads_reference_named_checkpoint(golden_dir):
+    from resshift_b200.models.unet import UNetModelSwin
+    from resshift_b200.weights import random_state_dict
+    gold = json.loads((golden_dir / "unet_keys_realsr.json").read_text())
+    ucfg, _ = preset("realsr")
+    m = UNetModelSwin(**ucfg.to_kwargs())
+    assert sorted(m.state_dict().keys()) == sorted(k for k, _, _ in gold["entries"])
+    m.load_state_dict(random_state_dict(ucfg, 1), strict=True)
+    # zero_module semantics of the reference constructor (models/unet.py:172-174) before loading
+    m2 = UNetModelSwin(**ucfg.to_kwargs())
+    assert float(m2.state_dict()["input_blocks.1.0.out_layers.3.weight"].abs().max()) == 0.0
+
+
+def test_cpu_call_fails_loudly():
+    from resshift_b200.models.unet import UNetModelSwin
+    ucfg, _ = preset("tiny")
+    m = UNetModelSwin(**ucfg.to_kwargs())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 64, 64), torch.zeros(1), lq=torch.zeros(1, 3, 64, 64))
+
+
+def test_diffusion_tables_match_oracle():
+    from oracle import diffusion_oracle as do
+    from resshift_b200.models.script_util import create_gaussian_diffusion
+    for name, steps in (("realsr", None), ("realsr_journal", None), ("realsr_journal", 15)):
+        _, d = preset(name, steps)
+        diff = create_gaussian_diffusion(**d.to_kwargs())
+        tabs = do.schedule_tables(do.eta_schedule(d.steps, d.min_noise_level, d.etas_end, d.kappa, d.schedule_kwargs["power"]), d.kappa)
+        np.testing.assert_allclose(diff.sqrt_etas, tabs["sqrt_etas"], rtol=1e-13)
+        np.testing.assert_allclose(diff.posterior_mean_coef1, tabs["coef1"], rtol=1e-13)
+        np.testing.assert_allclose(diff.posterior_mean_coef2, tabs["coef2"], rtol=1e-13)
+        np.testing.assert_allclose(diff.posterior_log_variance_clipped, tabs["log_var"], rtol=1e-13)
+        t = torch.arange(diff.num_timesteps)
+        np.testing.assert_allclose(diff._scale_input(torch.ones(diff.num_timesteps, 1), t)[:, 0].numpy(), tabs["in_scale"], rtol=1e-6)
+
+
+def test_timestep_respacing_map():
+    from resshift_b200.models.script_util import create_gaussian_diffusion
+    _, d = preset("realsr")
+    d.timestep_respacing = 5
+    diff = create_gaussian_diffusion(**d.to_kwargs())
+    assert diff.num_timesteps == 5 and diff.timestep_map == [0, 3, 6, 9, 12]
+
+
+def test_yaml_loader_resolves_interpolations(tmp_path):
+    from resshift_b200.sampler import load_yaml
+    p = tmp_path / "c.yaml"
+    p.write_text("autoencoder:\n  params:\n    embed_dim: 3\nmodel:\n  params:\n    out_channels: ${autoencoder.params.embed_dim}\n    lq_size: 64\n")
+    cfg = load_yaml(p)
+    assert cfg.model.params.out_channels == 3 and cfg.model.params["lq_size"] == 64

@@ -1,0 +1,173 @@
+"""GPU parity tests of the single operators, through the C ABI, against plain PyTorch fp32 on the same
+fp16-rounded operands.  Tolerances: the kernels keep fp32 accumulators and round once to fp16 on store,
+so the bound is one fp16 ulp of the result plus accumulation-order noise: |d| <= 2e-3 * max|ref| + 2e-3."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from tests import gpu_util as G
+    from resshift_b200 import _lib
+
+
+def _tol(ref):
+    return 2e-3 * ref.abs().max().item() + 2e-3
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, bn
+    (1, 8, 8, 64, 64, 1, 1, 0),          # one tile, one k-block
+    (2, 16, 16, 64, 32, 1, 1, 0),
+    (1, 16, 16, 128, 160, 1, 1, 0),      # N = 160 single UMMA
+    (2, 16, 16, 160, 192, 1, 1, 0),      # Cin not a multiple of 64 (zero-filled tail)
+    (1, 64, 64, 32, 32, 3, 1, 0),        # 3x3, bw=64
+    (2, 32, 32, 64, 96, 3, 1, 0),        # 3x3, bw=32
+    (3, 16, 16, 160, 320, 3, 1, 160),    # 2 channel tiles
+    (3, 8, 8, 320, 640, 3, 1, 0),        # box spans 2 images, odd batch (masked rows)
+    (2, 64, 64, 8, 160, 3, 1, 0),        # head conv: 8 (6 + pad) input channels
+    (2, 64, 64, 160, 3, 3, 1, 0),        # out conv: 3 output channels
+    (2, 32, 32, 64, 64, 3, 2, 0),        # stride 2 via parity views
+    (1, 64, 64, 160, 160, 3, 2, 0),
+    (16, 8, 8, 192, 576, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d(case, impl):
+    N, H, W, Ci, Co, k, s, bn = case
+    os.environ["RS_CONV_IMPL"] = impl
+    try:
+        g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000)
+        x = G.nhwc16(torch.randn(N, Ci, H, W, device="cuda", generator=g))
+        w = torch.randn(Co, Ci, k, k, device="cuda", generator=g) / (Ci * k * k) ** 0.5
+        b = torch.randn(Co, device="cuda", generator=g)
+        got = G.nchw32(G.conv2d(x, w, b, stride=s, bn=bn))
+        ref = G.ref_conv(x, w, b, stride=s)
+        st = G.err_stats(got, ref)
+        assert st["nan"] == 0 and st["max_abs"] <= _tol(ref), st
+    finally:
+        os.environ.pop("RS_CONV_IMPL", None)
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_conv2d_epilogue(act):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = G.nhwc16(torch.randn(2, 192, 16, 16, device="cuda", generator=g))
+    w = torch.randn(192, 192, 1, 1, device="cuda", generator=g) / 192 ** 0.5
+    b = torch.randn(192, device="cuda", generator=g)
+    res = G.nhwc16(torch.randn(2, 192, 16, 16, device="cuda", generator=g))
+    got = G.nchw32(G.conv2d(x, w, b, residual=res, act=act))
+    ref = G.ref_conv(x, w, b, residual=res, act=act)
+    st = G.err_stats(got, ref)
+    assert st["nan"] == 0 and st["max_abs"] <= _tol(ref), st
+    # fp32 NCHW output mode (the model head)
+    got32 = G.conv2d(x, w, b, act=0, out_f32=True)
+    ref32 = G.ref_conv(x, w, b)
+    assert (got32 - ref32).abs().max().item() <= 1e-3 * ref32.abs().max().item() + 1e-4
+
+
+def test_conv2d_channel_slices():
+    """Reads a channel slice of a wider buffer and writes into a slice of another (concat-free skips)."""
+    g = torch.Generator(device="cuda").manual_seed(6)
+    buf = G.nhwc16(torch.randn(2, 320, 16, 16, device="cuda", generator=g))
+    w = torch.randn(160, 160, 3, 3, device="cuda", generator=g) / (160 * 9) ** 0.5
+    b = torch.randn(160, device="cuda", generator=g)
+    obuf = torch.zeros(2, 16, 16, 480, dtype=torch.float16, device="cuda")
+    G.conv2d(None, w, b, in_view=(buf, 160, 160), out_view=(obuf, 320))
+    ref = G.ref_conv(buf[..., 160:].contiguous(), w, b)
+    got = G.nchw32(obuf[..., 320:].contiguous())
+    assert (got - ref).abs().max().item() <= _tol(ref)
+    assert obuf[..., :320].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("C,cfg", [(32, "plain"), (160, "silu"), (192, "plain"), (480, "film"), (1280, "film")])
+def test_groupnorm(C, cfg):
+    g = torch.Generator(device="cuda").manual_seed(C)
+    N, H, W = 3, 16, 16
+    x = G.nhwc16(torch.randn(N, C, H, W, device="cuda", generator=g) * 2 + 0.5)
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(C, device="cuda", generator=g)
+    film = torch.randn(N, 2 * C, device="cuda", generator=g) * 0.3 if cfg == "film" else None
+    silu = int(cfg != "plain")
+    y = torch.empty_like(x)
+    scratch = torch.empty(N * C * 2, dtype=torch.float32, device="cuda")
+    _lib.check(G.L.rs_op_groupnorm(x.data_ptr(), N, H, W, C, C, gamma.data_ptr(), beta.data_ptr(), _lib.ptr(film),
+                                   0 if film is None else 2 * C, silu, y.data_ptr(), C, scratch.data_ptr(), G.stream()))
+    torch.cuda.synchronize()
+    ref = F.group_norm(G.nchw32(x), 32, gamma, beta, eps=1e-5)
+    if film is not None:
+        ref = ref * (1 + film[:, :C, None, None]) + film[:, C:, None, None]
+    if silu:
+        ref = F.silu(ref)
+    st = G.err_stats(G.nchw32(y), ref)
+    assert st["nan"] == 0 and st["max_abs"] <= _tol(ref), st
+
+
+@pytest.mark.parametrize("impl", ["mma", "simt"])
+@pytest.mark.parametrize("shift", [0, 4])
+@pytest.mark.parametrize("hw", [(8, 8), (16, 32), (64, 64)])
+def test_window_attention(hw, shift, impl):
+    import sys
+    from oracle import unet_oracle as uo
+    from resshift_b200.arch import relative_position_index, shifted_window_mask
+    H, W = hw
+    if H == 8 and shift:
+        pytest.skip("no shifted windows at a single-window resolution")
+    heads, N = 6, 2
+    E = heads * 32
+    g = torch.Generator(device="cuda").manual_seed(H * 7 + shift)
+    qkv = (torch.randn(N, H, W, 3 * E, device="cuda", generator=g)).half()
+    table = torch.randn(225, heads, device="cuda", generator=g) * 0.5
+    dense = torch.empty(heads * 64 * 64, dtype=torch.float32, device="cuda")
+    _lib.check(G.L.rs_op_expand_relpos(table.data_ptr(), dense.data_ptr(), heads, G.stream()))
+    out = torch.empty(N, H, W, E, dtype=torch.float16, device="cuda")
+    os.environ["RS_ATTN_IMPL"] = impl
+    try:
+        _lib.check(G.L.rs_op_window_attention(qkv.data_ptr(), N, H, W, heads, shift, dense.data_ptr(), out.data_ptr(), G.stream()))
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("RS_ATTN_IMPL", None)
+    # reference: roll / partition / attention core / reverse / roll, fp32 on CPU (oracle pieces)
+    q = qkv.float().cpu()                                   # [N,H,W,3E]
+    y = q.permute(0, 3, 1, 2)
+    if shift:
+        y = torch.roll(y, (-shift, -shift), (2, 3))
+    yw = y.reshape(N, 3 * E, H // 8, 8, W // 8, 8).permute(0, 2, 4, 3, 5, 1).reshape(-1, 64, 3, heads, 32)
+    qq, kk, vv = (yw[:, :, i].transpose(1, 2) for i in range(3))
+    attn = (qq * 32 ** -0.5) @ kk.transpose(-2, -1)
+    idx = relative_position_index(8).reshape(-1)
+    attn = attn + table.cpu()[idx].view(64, 64, heads).permute(2, 0, 1)[None]
+    if shift:
+        m = shifted_window_mask(H, W, 8, shift)
+        nw = m.shape[0]
+        attn = (attn.view(-1, nw, heads, 64, 64) + m[None, :, None]).view(-1, heads, 64, 64)
+    o = (attn.softmax(-1) @ vv).transpose(1, 2).reshape(-1, 64, E)
+    o = o.view(N, H // 8, W // 8, 8, 8, E).permute(0, 5, 1, 3, 2, 4).reshape(N, E, H, W)
+    if shift:
+        o = torch.roll(o, (shift, shift), (2, 3))
+    ref = o.permute(0, 2, 3, 1)
+    st = G.err_stats(out.cpu(), ref)
+    assert st["nan"] == 0 and st["max_abs"] <= 4e-3 * ref.abs().max().item() + 2e-3, st
+
+
+def test_upsample_and_p_sample():
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(2, 8, 8, 64, device="cuda", generator=g).half()
+    y = torch.empty(2, 16, 16, 64, dtype=torch.float16, device="cuda")
+    _lib.check(G.L.rs_op_upsample2x(x.data_ptr(), 2, 8, 8, 64, y.data_ptr(), G.stream()))
+    ref = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest").permute(0, 2, 3, 1).half()
+    torch.cuda.synchronize()
+    assert torch.equal(y, ref)
+    a, b, n = (torch.randn(2, 3, 64, 64, device="cuda", generator=g) for _ in range(3))
+    out = torch.empty_like(a)
+    _lib.check(G.L.rs_p_sample(a.data_ptr(), b.data_ptr(), n.data_ptr(), out.data_ptr(), 0.8, 0.2, 0.5, 0, a.numel(), G.stream()))
+    torch.cuda.synchronize()
+    assert (out - (0.8 * a + 0.2 * b + 0.5 * n)).abs().max().item() < 1e-6
+    _lib.check(G.L.rs_p_sample(a.data_ptr(), b.data_ptr(), n.data_ptr(), out.data_ptr(), 0.8, 0.2, 0.5, 1, a.numel(), G.stream()))
+    torch.cuda.synchronize()
+    assert (out - (0.8 * a + 0.2 * b)).abs().max().item() < 1e-6
