@@ -78,6 +78,10 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def cpu_reference_images_per_s(steps_T: int, n_images: int, repeats: int):
     """The reference's algorithm for this path on the host cores: the CPU oracle (a torch fp32 restatement of
     UNetModelSwin.forward + p_sample, pinned to reference-generated goldens), all host threads."""
@@ -86,7 +90,8 @@ def cpu_reference_images_per_s(steps_T: int, n_images: int, repeats: int):
     from oracle import unet_oracle as uo
     from resshift_b200.config import preset
     from resshift_b200.weights import random_state_dict
-    torch.set_num_threads(os.cpu_count() or 1)
+    # torch's default intra-op thread count (= the cores this process may use); forcing os.cpu_count() threads
+    # inside a cgroup-limited container oversubscribes and stalls
     ucfg, dcfg = preset("realsr_journal", steps_T)
     sd = random_state_dict(ucfg, 0)
     tabs = do.schedule_tables(do.eta_schedule(dcfg.steps, dcfg.min_noise_level, dcfg.etas_end, dcfg.kappa,
@@ -130,6 +135,8 @@ def run_reference(args):
 
 
 def run_gpu(args):
+    import faulthandler
+    faulthandler.dump_traceback_later(600, exit=True)
     import torch
     import torch.distributed as dist
     from resshift_b200 import _lib
@@ -188,9 +195,11 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") ----------------------------------------------------
+    log(f"model + plan ready: {launches_per_forward} launches/forward, batch {B}")
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
+    log("warm-up done")
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -221,6 +230,7 @@ def run_gpu(args):
     def e2e_step():
         _lib.check(_lib.lib.rs_sampler_run_host(sampler, h_zy.data_ptr(), h_noise.data_ptr(), h_lq.data_ptr(), None,
                                                 h_out.data_ptr(), staging_ptr, staging_bytes, 1, stream))
+    log(f"device-resident: {ms_per_step:.2f} ms/step")
     for _ in range(3):
         e2e_step()
     barrier()
@@ -272,6 +282,7 @@ def run_gpu(args):
 
     # ---- CPU baseline: bounded sample on this box's host cores ----------------------------------------
     cpu = None
+    log("profile done; CPU baseline next")
     if not args.no_cpu_baseline:
         ips, times, cores = cpu_reference_images_per_s(T_STEPS, 1, 1)
         cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",

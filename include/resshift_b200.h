@@ -120,10 +120,19 @@ int rs_op_pack_conv_weight(const float* src_oihw, void* dst_f16, int O, int I, i
 int rs_op_conv2d(const void* x, int N, int H, int W, int C, int ld, const void* w_packed, int Ipad, const float* bias,
                  int Cout, int ksize, int stride, const void* residual, int res_ld, void* out, int out_ld,
                  float* out_f32_nchw, int act, int bn, void* stream);
+/* conv2d + GroupNorm partial statistics of its output (part[N][slots][cstride][2] at channel offset coff) */
+int rs_op_conv2d_stats(const void* x, int N, int H, int W, int C, int ld, const void* w_packed, int Ipad, const float* bias,
+                       int Cout, int ksize, int stride, const void* residual, int res_ld, void* out, int out_ld, int act,
+                       int bn, float* part, int cstride, int coff, int32_t* slots_out, void* stream);
+/* profiling aid: `iters` launches of the same conv; per-CTA timeline of the last one in dbg (8 x u64 per CTA) */
+int rs_op_conv2d_timeline(const void* x, int N, int H, int W, int C, int ld, const void* w_packed, int Ipad, const float* bias,
+                          int Cout, int ksize, int stride, void* out, int out_ld, int bn, int iters, void* dbg,
+                          int32_t* info, void* stream);
 /* GroupNorm32 (+ FiLM scale/shift, + SiLU) (reference models/basic_ops.py:15-17, models/unet.py:198-202) */
 int rs_op_groupnorm(const void* x, int N, int H, int W, int C, int ld, const float* gamma, const float* beta,
                     const float* film, long long film_sN, int silu, void* y, int y_ld, float* sums_scratch,
                     void* stream);
+long long rs_op_groupnorm_scratch_floats(int N, int H, int W, int C);
 /* window attention core (reference models/swin_transformer.py:114-145,251-275); qkv [N,H,W,3*heads*32] */
 int rs_op_expand_relpos(const float* table_225xh, float* dense_hx64x64, int heads, void* stream);
 int rs_op_window_attention(const void* qkv, int N, int H, int W, int heads, int shift, const float* bias_dense,

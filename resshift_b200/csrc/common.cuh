@@ -22,6 +22,7 @@ int fail(int code, const std::string& msg);
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \
     if (_e != cudaSuccess) {                                                                   \
+      (void)cudaGetLastError(); /* clear the error so later calls report their own */            \
       return ::rs::fail(-2, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + \
                                 __FILE__ + ":" + std::to_string(__LINE__) + ")");              \
     }                                                                                          \
@@ -55,6 +56,12 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+// Programmatic dependent launch: `pdl_trigger` lets the next kernel in the stream start its prologue
+// early; `pdl_wait` blocks until every prerequisite grid has completed and its writes are visible.
+// Every kernel of this library calls pdl_wait() before its first access to global memory.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 __device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
@@ -126,6 +133,21 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       "[%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// smem -> global tile store (bulk async group), coordinates clip out-of-bounds elements
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (TMA store reads them)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ----------------------------------------------------------------------------------------

@@ -51,6 +51,20 @@ struct ConvParams {
   long long out_sN, out_sH, out_sW;
   float* out_f32_nchw;               // optional fp32 NCHW output [Nimg, Cout, Hout, Wout]
   int act;
+  unsigned long long* dbg;           // optional per-CTA timeline (8 x u64 per CTA, globaltimer ns), profiling aid
+  // staged epilogue: results go to shared memory (128B-swizzled 64-column blocks) and leave through TMA stores;
+  // the residual tile arrives the same way through a TMA load
+  CUtensorMap tmOut, tmRes;
+  int tma_out;                       // 1: staged epilogue (fp16 NHWC output); 0: direct per-thread stores
+  int tma_res;
+  int epi_bc;                        // staging block width in columns: 64 / 32 / 16 (swizzle 128B / 64B / 32B),
+                                     // the largest that divides BN so a block never spills into the next channel tile
+  // fused GroupNorm statistics of the OUTPUT (per image, per 128-pixel tile slot, per channel: sum, sum of squares),
+  // written as deterministic partials [N][slots][cstride][2] for up to two consumers
+  float* gn_part[2];
+  int gn_cstride[2];
+  int gn_coff[2];
+  int gn_slots;
 };
 
 #ifdef __CUDACC__
@@ -65,10 +79,17 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* res_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  unsigned long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    dbg[0] = global_timer_ns(); dbg[7] = smid;
+  }
 
   // tile coordinates
   const int n_tile = blockIdx.x % p.n_tiles;
@@ -82,11 +103,14 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kMaxSrc; ++s) tma_prefetch_desc(&p.tmA[s]);
     tma_prefetch_desc(&p.tmB);
+    if (p.tma_out) tma_prefetch_desc(&p.tmOut);
+    if (p.tma_res) tma_prefetch_desc(&p.tmRes);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(res_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -97,6 +121,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
+  pdl_trigger();
+  pdl_wait();
+  if (dbg && threadIdx.x == 0) dbg[1] = global_timer_ns();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -124,6 +152,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
+      if (dbg && lane == 0 && kb == 0) dbg[2] = global_timer_ns();
       if (lane == 0) {
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
         const uint64_t adesc = umma_desc_sw128(sa);
@@ -139,6 +168,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
+    if (dbg && lane == 0) dbg[3] = global_timer_ns();
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
     const int quad = warp & 3;                       // warps 2,3,4,5 -> quadrants 2,3,0,1
@@ -152,8 +182,153 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (dbg && threadIdx.x == 64) dbg[4] = global_timer_ns();
 
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+
+    if (p.tma_out) {
+      // ---------- staged epilogue ----------
+      // All operand stages are free now (every MMA that read them has retired), so the pipeline smem is reused:
+      //   [block b] 128 rows x 128 B (64 fp16 columns), SWIZZLE_128B — first the residual tile (TMA load), then the
+      //   finished outputs written in place, then one TMA store per block;  after the blocks: per-warp GN partials.
+      const int bc = p.epi_bc;                       // columns per staging block
+      const int nblk = p.BN / bc;
+      const int blk_bytes = kConvBM * bc * 2;
+      const int bshift = (bc == 64) ? 6 : (bc == 32 ? 5 : 4);
+      // Swizzle<B,4,3>: the 16-byte unit index is XORed with address bits [7, 7+B); row pitch is 2*bc bytes
+      const int swz = (bc == 64) ? (r & 7) : (bc == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
+      uint8_t* sblk = smem;
+      float* wsum = reinterpret_cast<float*>(smem + (size_t)nblk * blk_bytes);         // [4 quads][BN][2]
+      const int etid = threadIdx.x - 64;                                              // 0..127 among epilogue threads
+      if (p.tma_res) {
+        if (etid == 0) {
+          mbar_arrive_expect_tx(res_bar, (uint32_t)(nblk * blk_bytes));
+          for (int b = 0; b < nblk; ++b)
+            tma_load_4d(sblk + (size_t)b * blk_bytes, &p.tmRes, res_bar, col0 + b * bc, w0, h0, n0);
+        }
+        mbar_wait(res_bar, 0);
+      }
+      const bool want_stats = p.gn_part[0] != nullptr;
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + c, v);
+        tmem_ld_wait();
+        const int col = col0 + c;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += (col + j < p.Cout) ? __ldg(p.bias + col + j) : 0.f;
+        }
+        if (p.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = gelu_erf_f(f[j]);
+        } else if (p.act == ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
+        }
+        // this thread's two 16-byte units inside the swizzled block
+        uint8_t* brow = sblk + (size_t)(c >> bshift) * blk_bytes + r * (2 * bc);
+        const int u0 = (c & (bc - 1)) >> 3;                  // 16-byte unit index of columns c..c+7 inside the block
+        uint4* a0 = reinterpret_cast<uint4*>(brow + (((u0) ^ swz) << 4));
+        uint4* a1 = reinterpret_cast<uint4*>(brow + (((u0 + 1) ^ swz) << 4));
+        if (p.tma_res) {
+          const uint4 r0 = *a0, r1 = *a1;
+          const __half2* h0p = reinterpret_cast<const __half2*>(&r0);
+          const __half2* h1p = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 x0 = __half22float2(h0p[j]);
+            const float2 x1 = __half22float2(h1p[j]);
+            f[2 * j] += x0.x; f[2 * j + 1] += x0.y;
+            f[8 + 2 * j] += x1.x; f[8 + 2 * j + 1] += x1.y;
+          }
+        }
+        uint4 o0, o1;
+        __half2* q0 = reinterpret_cast<__half2*>(&o0);
+        __half2* q1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          q0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+          q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+        }
+        *a0 = o0; *a1 = o1;
+        if (want_stats) {
+          // statistics of the values as stored (fp16-rounded), zero for rows / columns outside the tensor
+          float sv[16], sq[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 x0 = __half22float2(q0[j]);
+            const float2 x1 = __half22float2(q1[j]);
+            sv[2 * j] = x0.x; sv[2 * j + 1] = x0.y; sv[8 + 2 * j] = x1.x; sv[8 + 2 * j + 1] = x1.y;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (!row_ok || col + j >= p.Cout) sv[j] = 0.f;
+            sq[j] = sv[j] * sv[j];
+          }
+          // transpose-reduce over the 32 rows of this warp: 16 shuffles per moment
+#pragma unroll
+          for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+            const bool upper = (lane & bit) != 0;
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+              const float send_s = upper ? sv[j] : sv[j + half];
+              const float keep_s = upper ? sv[j + half] : sv[j];
+              sv[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+              const float send_q = upper ? sq[j] : sq[j + half];
+              const float keep_q = upper ? sq[j + half] : sq[j];
+              sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+            }
+          }
+          sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+          sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
+          if ((lane & 1) == 0) {
+            const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            wsum[((size_t)quad * p.BN + c + cidx) * 2] = sv[0];
+            wsum[((size_t)quad * p.BN + c + cidx) * 2 + 1] = sq[0];
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (etid == 0) {
+        for (int b = 0; b < nblk; ++b)
+          if (col0 + b * bc < p.Cout) tma_store_4d(&p.tmOut, sblk + (size_t)b * blk_bytes, col0 + b * bc, w0, h0, n0);
+        tma_store_commit();
+      }
+      if (want_stats) {
+        const int slot = th * p.tiles_w + tw;
+        for (int cc = etid; cc < p.BN; cc += 128) {
+          if (col0 + cc >= p.Cout) continue;
+          const float s0 = wsum[((size_t)0 * p.BN + cc) * 2], q0s = wsum[((size_t)0 * p.BN + cc) * 2 + 1];
+          const float s1 = wsum[((size_t)1 * p.BN + cc) * 2], q1s = wsum[((size_t)1 * p.BN + cc) * 2 + 1];
+          const float s2 = wsum[((size_t)2 * p.BN + cc) * 2], q2s = wsum[((size_t)2 * p.BN + cc) * 2 + 1];
+          const float s3 = wsum[((size_t)3 * p.BN + cc) * 2], q3s = wsum[((size_t)3 * p.BN + cc) * 2 + 1];
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            float* part = p.gn_part[d];
+            if (!part) continue;
+            const size_t ch = (size_t)p.gn_coff[d] + col0 + cc;
+            if (p.bn == 1) {
+              float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
+              dst[0] = (s0 + s1) + (s2 + s3);
+              dst[1] = (q0s + q1s) + (q2s + q3s);
+            } else {   // two images per tile: rows 0..63 -> n0, rows 64..127 -> n0 + 1
+              float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
+              dst[0] = s0 + s1; dst[1] = q0s + q1s;
+              if (n0 + 1 < p.Nimg) {
+                float* dst1 = part + (((size_t)(n0 + 1) * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
+                dst1[0] = s2 + s3; dst1[1] = q2s + q3s;
+              }
+            }
+          }
+        }
+      }
+      if (etid == 0) tma_store_wait_all();
+    } else {
+      // ---------- direct epilogue (fp32 NCHW model head, or RS_CONV_EPI=direct) ----------
     __half* orow = p.out ? p.out + n * p.out_sN + h * p.out_sH + w * p.out_sW : nullptr;
     const __half* rrow = p.residual ? p.residual + n * p.res_sN + h * p.res_sH + w * p.res_sW : nullptr;
 
@@ -218,11 +393,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
         }
       }
     }
+    }
   }
 
   // teardown: everyone done with TMEM before the allocating warp frees it
   tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[5] = global_timer_ns();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_dyn(tmem_base, (uint32_t)p.tmem_cols);
@@ -242,6 +419,8 @@ struct ConvSimtSrc {
 };
 
 __global__ void conv_simt_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ ConvSimtSrc s) {
+  pdl_trigger();
+  pdl_wait();
   // one warp per output pixel, lanes stride over output channels
   const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;

@@ -24,6 +24,8 @@ struct PackInputParams {
 };
 
 __global__ void pack_input_kernel(const PackInputParams p) {
+  pdl_trigger();
+  pdl_wait();
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)p.N * p.HW;
   if (pix >= total) return;
@@ -50,6 +52,8 @@ struct PackImageParams {
   int N, HW;
 };
 __global__ void pack_image_kernel(const PackImageParams p) {
+  pdl_trigger();
+  pdl_wait();
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= (long long)p.N * p.HW) return;
   const int n = (int)(pix / p.HW);
@@ -70,6 +74,8 @@ struct UpsampleParams {
   int N, H, W, C;
 };
 __global__ void upsample2x_kernel(const UpsampleParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int vecs = p.C >> 3;
   const long long total = (long long)p.N * (2 * p.H) * (2 * p.W) * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -89,6 +95,8 @@ __global__ void upsample2x_kernel(const UpsampleParams p) {
 // ResBlock.emb_layers = SiLU -> Linear, models/unet.py:161-167).  Tiny: one warp per output element.
 // ------------------------------------------------------------------------------------------------
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half_dim = dim / 2;
   if (i >= B * half_dim) return;
@@ -104,6 +112,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
 __global__ void linear_small_kernel(const float* __restrict__ x, const __half* __restrict__ W,
                                     const float* __restrict__ bias, float* __restrict__ out, int B, int K, int O,
                                     int silu_in, int silu_out) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B * O) return;
@@ -143,6 +153,8 @@ struct PSampleParams {
   __half* next_in; int next_cpad;     // optional: [N*HW, next_cpad]; channels [0, C) are written here
 };
 __global__ void p_sample_kernel(const PSampleParams p) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)p.N * p.C * p.HW;
   if (i >= total) return;
@@ -162,6 +174,8 @@ __global__ void p_sample_kernel(const PSampleParams p) {
 // prior_sample (reference models/gaussian_diffusion.py:517-529): x_T = z_y + kappa*sqrt_eta_T * noise
 __global__ void prior_sample_kernel(const float* __restrict__ zy, const float* __restrict__ noise,
                                     float* __restrict__ out, float coef, long long total) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) out[i] = zy[i] + coef * noise[i];
 }
@@ -171,6 +185,8 @@ __global__ void prior_sample_kernel(const float* __restrict__ zy, const float* _
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_conv_weight_kernel(const float* __restrict__ src, __half* __restrict__ dst, int O, int I,
                                         int KH, int KW, int Ipad) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)O * KH * KW * Ipad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -188,6 +204,8 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ src, __half* _
 // relative_position_bias_table [(2w-1)^2, heads] -> dense [heads][64][64] fp32 (window 8)
 // (reference models/swin_transformer.py:93-103 for the index, :127-130 for the gather)
 __global__ void expand_relpos_kernel(const float* __restrict__ table, float* __restrict__ dst, int heads) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= heads * 64 * 64) return;
   const int h = i / 4096, r = (i / 64) % 64, c = i % 64;
@@ -196,6 +214,8 @@ __global__ void expand_relpos_kernel(const float* __restrict__ table, float* __r
 }
 
 __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
 }

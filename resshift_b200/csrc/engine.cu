@@ -271,8 +271,10 @@ struct Op {
   // upsample
   View u_in, u_out;
   std::string w_name, b_name, g_name;   // parameter names resolved at bind
-  size_t stats_off = 0;                 // GroupNorm: offset of the [N][C][2] sums inside the stats region
+  size_t stats_off = 0;                 // GroupNorm: offset of its partial-sum buffer inside the stats region
   bool to_f32 = false;                  // conv: writes the fp32 NCHW model output
+  struct StatDst { int list; int op; int coff; };
+  std::vector<StatDst> stat_dst;        // conv: GroupNorm ops whose statistics this conv's epilogue produces
 };
 
 }  // namespace
@@ -322,7 +324,12 @@ struct Builder {
   rs_engine& E;
   std::vector<Op>* cur;
   size_t stats_off = 0;
+  struct Writer { long long off; int C; int list; int op; };
+  std::map<int, std::vector<Writer>> writers;      // tensor id -> latest conv writers by channel range
+  const bool fuse_stats = env_int("RS_GN_FUSE", 1) && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt");
   Builder(rs_plan& p) : P(p), E(*p.e), cur(&p.ops) {}
+  int list_id() const { return cur == &P.fe_ops ? 0 : 1; }
+  std::vector<Op>& list(int id) { return id == 0 ? P.fe_ops : P.ops; }
 
   int opi() const { return (int)(P.fe_ops.size() + P.ops.size()); }
 
@@ -337,16 +344,42 @@ struct Builder {
     const int i = opi();
     P.touch(in, i); if (out) P.touch(*out, i); if (res) P.touch(*res, i);
     cur->push_back(op);
+    if (out && !out_f32 && out->tens >= 0) {          // remember the latest writer of this channel range
+      auto& ws = writers[out->tens];
+      ws.erase(std::remove_if(ws.begin(), ws.end(), [&](const Writer& w) {
+                 return w.off < out->off + cout && out->off < w.off + w.C; }), ws.end());
+      ws.push_back({out->off, cout, list_id(), (int)cur->size() - 1});
+    }
   }
   void gn(const View& in, const std::string& name, const View& out, int silu, int film_off) {
     Op op; op.kind = OP_GN;
     op.gn.in = in; op.gn.out = out; op.gn.silu = silu; op.gn.film_off = film_off;
     op.g_name = name;
+    // can the producers' epilogues deliver the statistics?  (every channel of the view written by a conv of this plan)
+    bool fusable = false;
+    const int tile_slots = conv_tile_slots(in.H, in.W, &fusable);
+    std::vector<Writer> prod;
+    if (fuse_stats && fusable) {
+      int covered = 0;
+      auto it = writers.find(in.tens);
+      if (it != writers.end())
+        for (const Writer& w : it->second)
+          if (w.off >= in.off && w.off + w.C <= in.off + in.C) { prod.push_back(w); covered += w.C; }
+      bool ok = covered == in.C;
+      for (const Writer& w : prod) ok = ok && list(w.list)[w.op].stat_dst.size() < 2;
+      if (!ok) prod.clear();
+    }
+    int chunks, rows;
+    gn_chunks(in.H * in.W, in.N, &chunks, &rows);
+    op.gn.fused = !prod.empty();
+    op.gn.slots = op.gn.fused ? tile_slots : chunks;
     op.stats_off = stats_off;
-    stats_off += align_up((size_t)in.N * in.C * 2 * 4, 256);
+    stats_off += align_up((size_t)in.N * op.gn.slots * in.C * 2 * sizeof(float), 256);
     const int i = opi();
     P.touch(in, i); P.touch(out, i);
     cur->push_back(op);
+    for (const Writer& w : prod)
+      list(w.list)[w.op].stat_dst.push_back({list_id(), (int)cur->size() - 1, (int)(w.off - in.off)});
   }
   void attn(const View& qkv, const View& out, const std::string& blk, int shift) {
     Op op; op.kind = OP_ATTN; op.a_in = qkv; op.a_out = out; op.a_shift = shift;
@@ -580,6 +613,16 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
   rs_engine& E = *P.e;
   for (Op& op : ops) {
     if (op.kind == OP_CONV) {
+      for (int i = 0; i < 2; ++i) {
+        op.conv.gn_part[i] = nullptr;
+        if (i < (int)op.stat_dst.size()) {
+          const Op::StatDst& sd = op.stat_dst[i];
+          const Op& g = (sd.list == 0 ? P.fe_ops : P.ops)[sd.op];
+          op.conv.gn_part[i] = reinterpret_cast<float*>(P.ws + P.off_stats + g.stats_off);
+          op.conv.gn_cstride[i] = g.gn.in.C;
+          op.conv.gn_coff[i] = sd.coff;
+        }
+      }
       ConvDesc& d = op.conv;
       resolve(P, d.in); if (d.has_out) resolve(P, d.out); if (d.has_res) resolve(P, d.res);
       const Param* w = E.find(op.w_name);
@@ -595,8 +638,8 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       resolve(P, op.gn.in); resolve(P, op.gn.out);
       op.gn.gamma = E.at<float>(op.g_name + ".weight"); op.gn.beta = E.at<float>(op.g_name + ".bias");
       RS_CHECK(op.gn.gamma && op.gn.beta, "missing GroupNorm parameters " + op.g_name);
-      op.gn.sums = reinterpret_cast<float*>(P.ws + P.off_stats + op.stats_off);
-      P.launches += 2;
+      op.gn.part = reinterpret_cast<float*>(P.ws + P.off_stats + op.stats_off);
+      P.launches += op.gn.fused ? 1 : 2;
     } else if (op.kind == OP_ATTN) {
       resolve(P, op.a_in); resolve(P, op.a_out);
       op.a_bias = E.at<float>(op.w_name);
@@ -640,7 +683,7 @@ int run_ops(rs_plan& P, const std::vector<Op>& ops, const float* film_base, long
       case OP_UPSAMPLE: {
         UpsampleParams u{op.u_in.ptr, op.u_in.sN(), op.u_in.ld, op.u_out.ptr, op.u_in.N, op.u_in.H, op.u_in.W, op.u_in.C};
         const long long total = (long long)u.N * 4 * u.H * u.W * (u.C / 8);
-        upsample2x_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(u);
+        (void)launch_k(upsample2x_kernel, dim3((unsigned)std::min<long long>((total + 255) / 256, 148 * 16)), dim3(256), (size_t)(0), st, u);
         if (cudaGetLastError() != cudaSuccess) rc = fail(-2, "upsample launch failed");
         break;
       }
@@ -660,10 +703,10 @@ int run_embedding(rs_plan& P, const float* tsteps, int rows, cudaStream_t st) {
   float* vec = reinterpret_cast<float*>(P.ws + P.off_emb_vec);
   float* film = reinterpret_cast<float*>(P.ws + P.off_film);
   const int half = mc / 2;
-  timestep_embedding_kernel<<<(rows * half + 127) / 128, 128, 0, st>>>(tsteps, sinb, rows, mc);
+  (void)launch_k(timestep_embedding_kernel, dim3((rows * half + 127) / 128), dim3(128), (size_t)(0), st, tsteps, sinb, rows, mc);
   auto lin = [&](const float* x, const __half* W, const float* bias, float* out, int Kin, int O, int si, int so) {
     const long long warps = (long long)rows * O;
-    linear_small_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(x, W, bias, out, rows, Kin, O, si, so);
+    (void)launch_k(linear_small_kernel, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), (size_t)(0), st, x, W, bias, out, rows, Kin, O, si, so);
   };
   const Param* w0 = E.find("time_embed.0.weight");
   RS_CHECK(w0 && w0->ipad == mc, "time_embed.0 layout");
@@ -687,14 +730,14 @@ int pack_lq_and_input(rs_plan& P, const float* x, const float* lq, const float* 
     RS_CHECK(!c.cond_mask || mask != nullptr, "this model is mask-conditioned: mask must be given");
     PackImageParams ip{lq, 3, c.cond_mask ? mask : nullptr, c.cond_mask ? 1 : 0, P.fe_in.ptr, P.fe_cpad, P.B, P.lqH * P.lqW};
     const long long lpix = (long long)P.B * P.lqH * P.lqW;
-    pack_image_kernel<<<(unsigned)((lpix + 255) / 256), 256, 0, st>>>(ip);
+    (void)launch_k(pack_image_kernel, dim3((unsigned)((lpix + 255) / 256)), dim3(256), (size_t)(0), st, ip);
     int rc = run_ops(P, P.fe_ops, nullptr, 0, st); if (rc) return rc;
     pp.lq_nhwc = P.lq_feat.ptr; pp.lq_ld = P.lq_feat.ld; pp.Cl = P.lq_feat.C;
   } else {
     RS_CHECK(!c.cond_mask, "cond_mask with lq_size == image_size is not covered");
     pp.lq_nchw = lq; pp.Cl = 3;
   }
-  pack_input_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(pp);
+  (void)launch_k(pack_input_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), (size_t)(0), st, pp);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -750,15 +793,15 @@ int rs_unet_load_param(rs_engine* e, const char* name, const float* src, void* s
     const int O = p->shape[0], I = p->shape[1];
     const int KH = p->shape.size() == 4 ? p->shape[2] : 1, KW = p->shape.size() == 4 ? p->shape[3] : 1;
     const long long total = (long long)O * KH * KW * p->ipad;
-    pack_conv_weight_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(
+    (void)launch_k(pack_conv_weight_kernel, dim3((unsigned)std::min<long long>((total + 255) / 256, 4096)), dim3(256), (size_t)(0), st, 
         src, reinterpret_cast<__half*>(e->arena + p->off), O, I, KH, KW, p->ipad);
   } else if (p->role == R_RELPOS) {
     RS_CHECK(p->shape[0] == 225, "relative position table must be 15x15 (window 8)");
-    expand_relpos_kernel<<<(e->cfg.swin_heads * 4096 + 255) / 256, 256, 0, st>>>(
+    (void)launch_k(expand_relpos_kernel, dim3((e->cfg.swin_heads * 4096 + 255) / 256), dim3(256), (size_t)(0), st,
         src, reinterpret_cast<float*>(e->arena + p->off), e->cfg.swin_heads);
   } else {
     const long long n = p->shape[0];
-    copy_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, reinterpret_cast<float*>(e->arena + p->off), n);
+    (void)launch_k(copy_f32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), st, src, reinterpret_cast<float*>(e->arena + p->off), n);
   }
   RS_CUDA_OK(cudaGetLastError());
   return 0;
@@ -792,7 +835,7 @@ int rs_plan_bind(rs_plan* p, void* workspace_dev) {
   int rc = conv_init(); if (rc) return rc;
   rc = bind_ops(*p, p->fe_ops); if (rc) return rc;
   rc = bind_ops(*p, p->ops); if (rc) return rc;
-  p->launches += 6;   // memset is not a kernel; embedding (4) + pack (1-2)
+  p->launches += 6;   // embedding (4) + pack (1-2)
   p->bound = true;
   return 0;
 }
@@ -802,13 +845,12 @@ int rs_plan_forward(rs_plan* p, const float* x, const float* timesteps, const fl
   RS_CHECK(p && p->bound, "plan is not bound");
   RS_CHECK(x && timesteps && lq && out, "null tensor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  RS_CUDA_OK(cudaMemsetAsync(p->ws + p->off_stats, 0, p->stats_bytes, st));
   int rc = run_embedding(*p, timesteps, p->B, st); if (rc) return rc;
   rc = pack_lq_and_input(*p, x, lq, mask, nullptr, 0, st); if (rc) return rc;
   const float* film = reinterpret_cast<const float*>(p->ws + p->off_film);
   rc = run_ops(*p, p->ops, film, p->e->film_rows, st); if (rc) return rc;
   const long long n = (long long)p->B * p->e->cfg.out_channels * p->H * p->W;
-  copy_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->out_f32, out, n);
+  (void)launch_k(copy_f32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), st, p->out_f32, out, n);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -820,7 +862,6 @@ int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const fl
                     double* ms_by_kind, double* conv_flops, int32_t* n_conv_launches, void* stream) {
   RS_CHECK(p && p->bound && ms_by_kind, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  RS_CUDA_OK(cudaMemsetAsync(p->ws + p->off_stats, 0, p->stats_bytes, st));
   int rc = run_embedding(*p, timesteps, p->B, st); if (rc) return rc;
   rc = pack_lq_and_input(*p, x, lq, mask, nullptr, 0, st); if (rc) return rc;
   Prof prof;
@@ -846,6 +887,8 @@ int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const fl
 }
 
 __global__ void probe_kernel(const __half* src, long long sN, int ld, float* dst, int N, int HW, int C) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * C * HW) return;
   const int hw = (int)(i % HW); const int c = (int)((i / HW) % C); const int n = (int)(i / ((long long)HW * C));
@@ -860,7 +903,7 @@ int rs_plan_probe(rs_plan* p, const char* block, float* dst, int32_t* channels, 
   if (channels) *channels = v.C; if (h) *h = v.H; if (w) *w = v.W;
   if (dst) {
     const long long n = (long long)v.N * v.C * v.H * v.W;
-    probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(v.ptr, v.sN(), v.ld, dst, v.N, v.H * v.W, v.C);
+    (void)launch_k(probe_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), v.ptr, v.sN(), v.ld, dst, v.N, v.H * v.W, v.C);
     RS_CUDA_OK(cudaGetLastError());
   }
   return 0;
@@ -880,6 +923,7 @@ struct rs_sampler {
   bool tables_uploaded = false;
   float* tap_pred = nullptr; float* tap_sample = nullptr;
   cudaGraphExec_t graph = nullptr;
+  cudaStream_t cap_stream = nullptr;     // capture happens on a private stream (the legacy default stream cannot capture)
   const void* g_zy = nullptr; const void* g_noise = nullptr; const void* g_lq = nullptr; const void* g_mask = nullptr;
   void* g_out = nullptr;
 };
@@ -898,13 +942,12 @@ int sampler_enqueue(rs_sampler& S, const float* z_y, const float* noises, const 
   const float* coef1 = tab, *coef2 = tab + 1024, *stdv = tab + 2048, *in_scale = tab + 3072;
   (void)lat;
   // x_T = z_y + kappa * sqrt_eta_T * noise_0   (prior_sample)
-  prior_sample_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, st>>>(z_y, noises, x_t, S.prior_coef, numel);
+  (void)launch_k(prior_sample_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), (size_t)(0), st, z_y, noises, x_t, S.prior_coef, numel);
   // LQ feature (once) + first packed input, scaled by in_scale[T-1]
   int rc = pack_lq_and_input(P, x_t, lq, mask, in_scale, S.T - 1, st); if (rc) return rc;
   const float* film_all = reinterpret_cast<const float*>(P.ws + P.off_film);
   for (int k = 0; k < S.T; ++k) {
     const int t = S.T - 1 - k;
-    RS_CUDA_OK(cudaMemsetAsync(P.ws + P.off_stats, 0, P.stats_bytes, st));
     rc = run_ops(P, P.ops, film_all + (long long)t * P.e->film_rows, 0, st); if (rc) return rc;
     PSampleParams pp{};
     pp.x_t = x_t; pp.x0 = P.out_f32; pp.noise = noises + (long long)(k + 1) * numel;
@@ -913,7 +956,7 @@ int sampler_enqueue(rs_sampler& S, const float* z_y, const float* noises, const 
     pp.N = P.B; pp.C = c.in_channels; pp.HW = P.H * P.W;
     pp.next_in = P.xin.ptr; pp.next_cpad = P.cin_pad;
     if (S.tap_pred) RS_CUDA_OK(cudaMemcpyAsync(S.tap_pred + (long long)k * numel, P.out_f32, numel * 4, cudaMemcpyDeviceToDevice, st));
-    p_sample_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, st>>>(pp);
+    (void)launch_k(p_sample_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), (size_t)(0), st, pp);
     if (S.tap_sample) RS_CUDA_OK(cudaMemcpyAsync(S.tap_sample + (long long)k * numel, pp.x_next, numel * 4, cudaMemcpyDeviceToDevice, st));
   }
   RS_CUDA_OK(cudaGetLastError());
@@ -968,6 +1011,7 @@ int rs_sampler_create(rs_plan* p, int steps, const double* sqrt_etas, double kap
 }
 void rs_sampler_destroy(rs_sampler* s) {
   if (s && s->graph) cudaGraphExecDestroy(s->graph);
+  if (s && s->cap_stream) cudaStreamDestroy(s->cap_stream);
   delete s;
 }
 int rs_sampler_set_taps(rs_sampler* s, float* pred, float* sample) {
@@ -988,9 +1032,10 @@ int rs_sampler_run(rs_sampler* s, const float* z_y, const float* noises, const f
   }
   if (!s->graph) {
     cudaGraph_t g = nullptr;
-    RS_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = sampler_enqueue(*s, z_y, noises, lq, mask, out_latent, st);
-    cudaError_t ce = cudaStreamEndCapture(st, &g);
+    if (!s->cap_stream) RS_CUDA_OK(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+    RS_CUDA_OK(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = sampler_enqueue(*s, z_y, noises, lq, mask, out_latent, s->cap_stream);
+    cudaError_t ce = cudaStreamEndCapture(s->cap_stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     RS_CUDA_OK(ce);
     RS_CUDA_OK(cudaGraphInstantiate(&s->graph, g, 0));
@@ -1040,6 +1085,8 @@ int rs_sampler_run_host(rs_sampler* s, const float* z_y_h, const float* noises_h
 
 __global__ void p_sample_flat_kernel(const float* x, const float* x0, const float* nz, float* out, float c1, float c2,
                                      float sd, int t0, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = c1 * x[i] + c2 * x0[i];
@@ -1049,7 +1096,7 @@ __global__ void p_sample_flat_kernel(const float* x, const float* x0, const floa
 int rs_p_sample(const float* x_t, const float* x0, const float* noise, float* x_next, float c1, float c2, float sd,
                 int t_is_zero, long long numel, void* stream) {
   RS_CHECK(x_t && x0 && noise && x_next && numel > 0, "bad argument");
-  p_sample_flat_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  (void)launch_k(p_sample_flat_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       x_t, x0, noise, x_next, c1, c2, sd, t_is_zero, numel);
   RS_CUDA_OK(cudaGetLastError());
   return 0;

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -44,17 +45,20 @@ struct View {
 
 // 4-D activation map {C, W, H, N} with explicit element strides; box {64, bw, bh, bn}, 128B swizzle.
 inline int encode_act_map(CUtensorMap* m, const __half* base, int C, int W, int H, int N, long long sW,
-                          long long sH, long long sN, int bw, int bh, int bn) {
+                          long long sH, long long sN, int bw, int bh, int bn, int box_c = kConvBK) {
   PFN_encodeTiled enc = get_encode_tiled();
   RS_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kConvBK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  const CUtensorMapSwizzle swz = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  RS_CHECK(box_c == 64 || box_c == 32 || box_c == 16, "activation box width");
   cuuint32_t estr[4] = {1, 1, 1, 1};
   RS_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "activation base must be 16-byte aligned");
   RS_CHECK(sW % 8 == 0 && sH % 8 == 0 && sN % 8 == 0, "activation strides must be multiples of 16 bytes");
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed with CUresult " + std::to_string((int)r));
   return 0;
@@ -84,6 +88,22 @@ inline bool env_is(const char* name, const char* val) {
   return v && std::strcmp(v, val) == 0;
 }
 
+// All kernels go through this launcher: cudaLaunchKernelEx with the programmatic-stream-serialization
+// attribute (PDL), so kernel N+1's prologue overlaps kernel N's tail, also inside captured graphs.
+// RS_PDL=0 turns the attribute off.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  static const int use_pdl = env_int("RS_PDL", 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 inline int pow2_floor_div(int x, int cap) {   // largest power of two dividing x, capped
   int p = 1;
   while (p * 2 <= cap && x % (p * 2) == 0) p *= 2;
@@ -104,6 +124,11 @@ struct ConvDesc {
   float* out_f32 = nullptr;
   int act = ACT_NONE;
   int bn_override = 0;
+  unsigned long long* dbg = nullptr;
+  // fused GroupNorm partial statistics of the output (up to two consumers)
+  float* gn_part[2] = {nullptr, nullptr};
+  int gn_cstride[2] = {0, 0};
+  int gn_coff[2] = {0, 0};
   // filled by finalize()
   ConvParams prm;
   ConvSimtSrc simt;
@@ -188,6 +213,31 @@ inline int conv_finalize(ConvDesc& d) {
     RS_CHECK(d.out.ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d.out.ptr) & 15) == 0, "output alignment");
   }
   p.out_f32_nchw = d.out_f32;
+  p.dbg = d.dbg;
+  // staged epilogue (TMA store / TMA residual load) for fp16 NHWC outputs
+  p.tma_out = (d.has_out && !d.out_f32 && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt")) ? 1 : 0;
+  p.tma_res = (p.tma_out && d.has_res) ? 1 : 0;
+  p.epi_bc = (BN % 64 == 0) ? 64 : (BN % 32 == 0 ? 32 : 16);
+  if (p.tma_out) {
+    int rc = encode_act_map(&p.tmOut, d.out.ptr, d.Cout, Wout, Hout, N, d.out.sW(), d.out.sH(), d.out.sN(), p.bw, p.bh, p.bn, p.epi_bc);
+    if (rc) return rc;
+    if (p.tma_res) {
+      rc = encode_act_map(&p.tmRes, d.res.ptr, d.Cout, Wout, Hout, N, d.res.sW(), d.res.sH(), d.res.sN(), p.bw, p.bh, p.bn, p.epi_bc);
+      if (rc) return rc;
+    }
+    // the staging area (column blocks + per-warp GN partials) must fit in the operand ring
+    const size_t need = (size_t)BN * kConvBM * 2 + (size_t)4 * BN * 2 * sizeof(float);
+    RS_CHECK(need <= (size_t)stages * stage_bytes, "epilogue staging does not fit in the pipeline shared memory");
+  }
+  p.gn_slots = p.tiles_w * p.tiles_h;
+  RS_CHECK(!(d.gn_part[0] || d.gn_part[1]) || p.bn <= 2, "fused GroupNorm statistics need tiles of at most two images");
+  for (int i = 0; i < 2; ++i) {
+    p.gn_part[i] = p.tma_out ? d.gn_part[i] : nullptr;
+    p.gn_cstride[i] = d.gn_cstride[i]; p.gn_coff[i] = d.gn_coff[i];
+  }
+  if (p.gn_part[0] == nullptr && p.gn_part[1] != nullptr) {
+    p.gn_part[0] = p.gn_part[1]; p.gn_cstride[0] = p.gn_cstride[1]; p.gn_coff[0] = p.gn_coff[1]; p.gn_part[1] = nullptr;
+  }
   // tensor maps + SIMT mirrors
   ConvSimtSrc& s = d.simt;
   std::memset(&s, 0, sizeof(s));
@@ -224,38 +274,59 @@ inline int conv_launch(const ConvDesc& d, cudaStream_t st) {
   if (env_is("RS_CONV_IMPL", "simt")) {
     const long long npix = (long long)d.prm.Nimg * d.prm.Hout * d.prm.Wout;
     const int warps = 8;
-    conv_simt_kernel<<<(unsigned)((npix + warps - 1) / warps), warps * 32, 0, st>>>(d.prm, d.simt);
+    (void)launch_k(conv_simt_kernel, dim3((unsigned)((npix + warps - 1) / warps)), dim3(warps * 32), (size_t)(0), st, d.prm, d.simt);
   } else {
-    conv_gemm_sm100_kernel<<<d.grid, kConvThreads, d.smem, st>>>(d.prm);
+    (void)launch_k(conv_gemm_sm100_kernel, dim3(d.grid), dim3(kConvThreads), (size_t)(d.smem), st, d.prm);
   }
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 // ---- GroupNorm -------------------------------------------------------------------------------
+// number of 128-pixel tile slots per image the conv kernel uses for an H x W output (and whether its epilogue can
+// produce per-image statistics: tiles must not span more than two images)
+inline int conv_tile_slots(int H, int W, bool* fusable = nullptr) {
+  const int bw = pow2_floor_div(W, kConvBM);
+  const int bh = pow2_floor_div(H, kConvBM / bw);
+  if (fusable) *fusable = (kConvBM / (bw * bh)) <= 2;
+  return (W / bw) * (H / bh);
+}
+
 struct GnDesc {
   View in, out;
   const float* gamma = nullptr; const float* beta = nullptr;
   const float* film = nullptr; long long film_sN = 0;   // resolved per launch for FiLM layers
   int film_off = -1;      // offset of this layer's [2C] slice inside an embedding row, or -1
   int silu = 0;
-  float* sums = nullptr;  // [N][C][2]
+  float* part = nullptr;  // [N][slots][C][2]
+  int slots = 0;
+  bool fused = false;     // statistics already written by the producing conv kernels
 };
+
+inline void gn_chunks(int HW, int N, int* chunks, int* rows) {
+  // enough CTAs to fill the machine, at least 32 rows each
+  int c = std::max(1, std::min((HW + 31) / 32, (148 * 4 + N - 1) / N));
+  int r = (HW + c - 1) / c;
+  *chunks = (HW + r - 1) / r; *rows = r;
+}
 
 inline int gn_launch(const GnDesc& g, cudaStream_t st) {
   const int C = g.in.C, HW = g.in.H * g.in.W, N = g.in.N;
   RS_CHECK(C % 32 == 0 && C % 8 == 0 && C <= 2048, "GroupNorm channel count");
   RS_CHECK(g.in.ld % 8 == 0 && g.out.ld % 8 == 0, "GroupNorm view alignment");
-  // enough CTAs to fill the machine, at least 32 rows each
-  int chunks = std::max(1, std::min((HW + 31) / 32, (148 * 4 + N - 1) / N));
-  int rows = (HW + chunks - 1) / chunks;
-  chunks = (HW + rows - 1) / rows;
-  GnStatsParams sp{g.in.ptr, g.in.sN(), g.in.ld, C, HW, N, g.sums, rows};
-  gn_stats_kernel<<<dim3(chunks, N), 256, 2 * C * sizeof(float), st>>>(sp);
-  RS_CUDA_OK(cudaGetLastError());
-  GnApplyParams ap{g.in.ptr, g.in.sN(), g.in.ld, g.out.ptr, g.out.sN(), g.out.ld, C, HW, N, g.sums,
+  int chunks, rows;
+  gn_chunks(HW, N, &chunks, &rows);
+  int slots = g.slots;
+  if (!g.fused) {
+    slots = chunks;
+    const int lanes = 256 / (C / 8);
+    GnStatsParams sp{g.in.ptr, g.in.sN(), g.in.ld, C, HW, N, g.part, slots, rows};
+    (void)launch_k(gn_stats_kernel, dim3(chunks, N), dim3(256), (size_t)lanes * C * 2 * sizeof(float), st, sp);
+    RS_CUDA_OK(cudaGetLastError());
+  }
+  GnApplyParams ap{g.in.ptr, g.in.sN(), g.in.ld, g.out.ptr, g.out.sN(), g.out.ld, C, HW, N, g.part, slots,
                    g.gamma, g.beta, g.film, g.film_sN, g.silu, rows, 1e-5f};
-  gn_apply_kernel<<<dim3(chunks, N), 256, 2 * C * sizeof(float), st>>>(ap);
+  (void)launch_k(gn_apply_kernel, dim3(chunks, N), dim3(256), (size_t)(2 * C + 64) * sizeof(float), st, ap);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -266,7 +337,7 @@ inline int attn_launch(const View& qkv, const View& out, const float* bias, int 
   RS_CHECK(E == heads * 32, "window attention kernel is specialised for head_dim 32");
   WinAttnParams p{qkv.ptr, qkv.ld, out.ptr, out.ld, bias, qkv.N, qkv.H, qkv.W, heads, E, shift,
                   0.17677669529663687f, env_is("RS_ATTN_IMPL", "simt") ? 1 : 0};
-  window_attn_kernel<<<dim3(qkv.N * (qkv.H / 8) * (qkv.W / 8), heads), 128, 0, st>>>(p);
+  (void)launch_k(window_attn_kernel, dim3(dim3(qkv.N * (qkv.H / 8) * (qkv.W / 8), heads)), dim3(128), (size_t)(0), st, p);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }

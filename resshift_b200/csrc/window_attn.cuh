@@ -52,6 +52,8 @@ __device__ __forceinline__ int swin_label(int wy, int c, int H, int shift) {
 constexpr int kAttnPad = 40;   // halves per smem row (32 + 8 pad: conflict-free 32-bit fragment reads)
 
 __global__ void __launch_bounds__(128) window_attn_kernel(const WinAttnParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) __half sQ[64 * kAttnPad];
   __shared__ __align__(16) __half sK[64 * kAttnPad];
   __shared__ __align__(16) __half sVt[32 * 72];        // V transposed: [d][token], 64 + 8 pad

@@ -46,7 +46,10 @@ def test_conv2d(case, impl):
         x = G.nhwc16(torch.randn(N, Ci, H, W, device="cuda", generator=g))
         w = torch.randn(Co, Ci, k, k, device="cuda", generator=g) / (Ci * k * k) ** 0.5
         b = torch.randn(Co, device="cuda", generator=g)
-        got = G.nchw32(G.conv2d(x, w, b, stride=s, bn=bn))
+        if Co % 8:          # the 3-channel model head writes fp32 NCHW (fp16 views need 16-byte rows)
+            got = G.conv2d(x, w, b, stride=s, bn=bn, out_f32=True)
+        else:
+            got = G.nchw32(G.conv2d(x, w, b, stride=s, bn=bn))
         ref = G.ref_conv(x, w, b, stride=s)
         st = G.err_stats(got, ref)
         assert st["nan"] == 0 and st["max_abs"] <= _tol(ref), st
@@ -85,6 +88,43 @@ def test_conv2d_channel_slices():
     assert obuf[..., :320].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("case", [(2, 64, 64, 64, 160, 3), (3, 16, 16, 160, 320, 3), (3, 8, 8, 320, 640, 1), (5, 8, 8, 64, 32, 3)])
+def test_conv2d_fused_groupnorm_statistics(case):
+    """The conv epilogue's per-(image, tile slot, channel) partial sums must add up to the sums of the stored fp16
+    output, written at a channel offset of a wider statistics buffer (concat consumers), and be bit-reproducible."""
+    import ctypes as C
+    N, H, W, Ci, Co, k = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = G.nhwc16(torch.randn(N, Ci, H, W, device="cuda", generator=g))
+    w = torch.randn(Co, Ci, k, k, device="cuda", generator=g) / (Ci * k * k) ** 0.5
+    b = torch.randn(Co, device="cuda", generator=g)
+    res = G.nhwc16(torch.randn(N, Co, H, W, device="cuda", generator=g))
+    wp, ipad = G.pack_weight(w)
+    cstride, coff = Co + 32, 32
+    outs, parts = [], []
+    for rep in range(2):
+        out = torch.empty(N, H, W, Co, dtype=torch.float16, device="cuda")
+        part = torch.full((N * 64 * cstride * 2,), float("nan"), dtype=torch.float32, device="cuda")
+        slots = C.c_int32()
+        _lib.check(G.L.rs_op_conv2d_stats(x.data_ptr(), N, H, W, Ci, Ci, wp.data_ptr(), ipad, b.data_ptr(), Co, k, 1,
+                                          res.data_ptr(), Co, out.data_ptr(), Co, 0, 0, part.data_ptr(), cstride, coff,
+                                          C.byref(slots), G.stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+        parts.append(part[:N * slots.value * cstride * 2].view(N, slots.value, cstride, 2)[:, :, coff:coff + Co].clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(parts[0], parts[1])         # deterministic
+    ref = G.ref_conv(x, w, b, residual=res)
+    assert (G.nchw32(outs[0]) - ref).abs().max().item() <= _tol(ref)
+    of = outs[0].float()
+    s_ref = of.sum(dim=(1, 2))                                                       # [N, Co]
+    q_ref = (of * of).sum(dim=(1, 2))
+    s_got = parts[0][..., 0].sum(dim=1)
+    q_got = parts[0][..., 1].sum(dim=1)
+    assert not torch.isnan(parts[0]).any()
+    assert (s_got - s_ref).abs().max().item() <= 1e-3 * (1 + s_ref.abs().max().item())
+    assert (q_got - q_ref).abs().max().item() <= 1e-4 * q_ref.abs().max().item()
+
+
 @pytest.mark.parametrize("C,cfg", [(32, "plain"), (160, "silu"), (192, "plain"), (480, "film"), (1280, "film")])
 def test_groupnorm(C, cfg):
     g = torch.Generator(device="cuda").manual_seed(C)
@@ -95,7 +135,7 @@ def test_groupnorm(C, cfg):
     film = torch.randn(N, 2 * C, device="cuda", generator=g) * 0.3 if cfg == "film" else None
     silu = int(cfg != "plain")
     y = torch.empty_like(x)
-    scratch = torch.empty(N * C * 2, dtype=torch.float32, device="cuda")
+    scratch = torch.empty(G.L.rs_op_groupnorm_scratch_floats(N, H, W, C), dtype=torch.float32, device="cuda")
     _lib.check(G.L.rs_op_groupnorm(x.data_ptr(), N, H, W, C, C, gamma.data_ptr(), beta.data_ptr(), _lib.ptr(film),
                                    0 if film is None else 2 * C, silu, y.data_ptr(), C, scratch.data_ptr(), G.stream()))
     torch.cuda.synchronize()

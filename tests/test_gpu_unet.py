@@ -157,9 +157,17 @@ def test_batch_independence_at_bench_size():
     assert not torch.isnan(full).any()
     for i in (0, 5, 15):
         one = m(x[i:i + 1], t[i:i + 1], lq=lq[i:i + 1])
-        d = (one - full[i:i + 1]).abs().max().item()
-        print(f"[property] batch-16 vs single image {i}: max|d|={d:.3e}")
-        assert d <= 2e-3      # not bit-exact: atomics order in GroupNorm sums, different channel tiling
+        d = (one - full[i:i + 1]).abs()
+        print(f"[property] batch-16 vs single image {i}: max|d|={d.max().item():.3e} mean|d|={d.mean().item():.3e}")
+        # every reduction has a fixed order (no atomics) and per-image statistics never mix images, so a batched
+        # run must reproduce the single-image run bit for bit
+        assert d.max().item() == 0.0
+    # and the batched result itself is right: image 5 against the CPU oracle
+    from oracle import unet_oracle as uo
+    sd = random_state_dict(ucfg, 0)
+    ref = uo.unet_forward(sd, ucfg, x[5:6].cpu(), t[5:6].cpu(), lq=lq[5:6].cpu())
+    mx, mn = _report("forward realsr, image 5 of a batch of 16", full[5:6], ref)
+    assert mx <= FWD_MAX and mn <= FWD_MEAN
 
 
 def test_graph_replay_is_deterministic_and_matches_eager():
@@ -173,8 +181,8 @@ def test_graph_replay_is_deterministic_and_matches_eager():
     a = diff.sample_latent(y, m, {"lq": y}, noises=noises, use_graph=True)
     b = diff.sample_latent(y, m, {"lq": y}, noises=noises, use_graph=True)
     c = diff.sample_latent(y, m, {"lq": y}, noises=noises, use_graph=False)
-    assert (a - b).abs().max().item() <= 1e-3
-    assert (a - c).abs().max().item() <= 1e-3
+    assert torch.equal(a, b)          # graph replay is bit-reproducible
+    assert torch.equal(a, c)          # and identical to the eagerly enqueued loop
 
 
 def test_sampler_class_end_to_end_with_identity_autoencoder():
