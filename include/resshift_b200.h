@@ -82,6 +82,9 @@ int rs_plan_forward(rs_plan* p, const float* x, const float* timesteps, const fl
  * GroupNorm, window attention, upsample; conv_flops = algorithmic 2*MACs executed by the GEMM kernel. */
 int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const float* lq, const float* mask,
                     double* ms_by_kind, double* conv_flops, int32_t* n_conv_launches, void* stream);
+/* per-operator variant: ms[i] and desc[i*desc_stride] for the first `cap` operators of the forward program */
+int rs_plan_profile_ops(rs_plan* p, const float* x, const float* timesteps, const float* lq, const float* mask,
+                        double* ms, char* desc, int desc_stride, int cap, int32_t* n_ops, void* stream);
 /* debugging aid: copy an intermediate block output ("input_blocks.3", "middle_block", "output_blocks.11")
  * as fp32 NCHW into dst (device); returns channel count through *channels.  Valid right after a forward
  * only for blocks whose buffer is still live; used by the parity tests. */

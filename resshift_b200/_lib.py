@@ -51,6 +51,7 @@ _SIGNATURES = {
     "rs_plan_num_launches": (C.c_int, [_P]),
     "rs_plan_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "rs_plan_profile": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), _P]),
+    "rs_plan_profile_ops": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_double), C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int32), _P]),
     "rs_plan_probe": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
     "rs_sampler_create": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_int32), C.POINTER(_P)]),
     "rs_sampler_destroy": (None, [_P]),

@@ -886,6 +886,40 @@ int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const fl
   return 0;
 }
 
+// Per-operator timing of one forward: fills ms[i] and a short description for each op of the main program.
+int rs_plan_profile_ops(rs_plan* p, const float* x, const float* timesteps, const float* lq, const float* mask,
+                        double* ms, char* desc, int desc_stride, int cap, int32_t* n_ops, void* stream) {
+  RS_CHECK(p && p->bound && ms && desc && n_ops, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = run_embedding(*p, timesteps, p->B, st); if (rc) return rc;
+  rc = pack_lq_and_input(*p, x, lq, mask, nullptr, 0, st); if (rc) return rc;
+  Prof prof;
+  const float* film = reinterpret_cast<const float*>(p->ws + p->off_film);
+  rc = run_ops(*p, p->ops, film, p->e->film_rows, st, &prof); if (rc) return rc;
+  RS_CUDA_OK(cudaStreamSynchronize(st));
+  const int n = std::min<int>((int)p->ops.size(), cap);
+  *n_ops = n;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, prof.ev[2 * i], prof.ev[2 * i + 1]);
+    ms[i] = t;
+    const Op& op = p->ops[i];
+    char* d = desc + (size_t)i * desc_stride;
+    if (op.kind == OP_CONV) {
+      const ConvParams& c = op.conv.prm;
+      snprintf(d, desc_stride, "conv%dx%d s%d %dx%d Cin=%d Cout=%d grid=%d BN=%d st=%d %s", op.conv.ksize, op.conv.ksize,
+               op.conv.stride, c.Hout, c.Wout, op.conv.in.C, c.Cout, op.conv.grid, c.BN, c.stages, op.w_name.c_str());
+    } else if (op.kind == OP_GN) {
+      snprintf(d, desc_stride, "gn %dx%d C=%d fused=%d %s", op.gn.in.H, op.gn.in.W, op.gn.in.C, (int)op.gn.fused, op.g_name.c_str());
+    } else if (op.kind == OP_ATTN) {
+      snprintf(d, desc_stride, "attn %dx%d shift=%d", op.a_in.H, op.a_in.W, op.a_shift);
+    } else {
+      snprintf(d, desc_stride, "upsample %dx%d C=%d", op.u_in.H, op.u_in.W, op.u_in.C);
+    }
+  }
+  return 0;
+}
+
 __global__ void probe_kernel(const __half* src, long long sN, int ld, float* dst, int N, int HW, int C) {
   pdl_trigger();
   pdl_wait();
