@@ -11,7 +11,7 @@
 //   tensor maps over the same buffer (no copy); each tap names its map.
 // * weights are [Cout][tap][Cin_pad] fp16 (K-major), one 2-D tensor map.
 // * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-//   warps 2..5 = epilogue (TMEM -> registers -> bias / activation / residual -> global).
+//   warps 2..9 = epilogue (TMEM -> registers -> bias / activation / residual -> global).
 // * covers reference call sites: every nn.Conv2d / nn.Linear inside UNetModelSwin.forward
 //   (reference models/unet.py:147,173,184,707,862,69,99-101; models/swin_transformer.py:22-24,105-107,480,515).
 #pragma once
@@ -22,7 +22,8 @@ namespace rs {
 
 constexpr int kConvBM = 128;      // pixels per tile (UMMA M)
 constexpr int kConvBK = 64;       // channels per k-block (128 B rows, SWIZZLE_128B)
-constexpr int kConvThreads = 192;
+constexpr int kConvEpiWarps = 8;   // two warps per TMEM lane quadrant, interleaved over the 16-column chunks
+constexpr int kConvThreads = 64 + 32 * kConvEpiWarps;
 constexpr int kMaxTaps = 9;
 constexpr int kMaxSrc = 4;
 
@@ -43,6 +44,9 @@ struct ConvParams {
   int BN, n_tiles, Cout;
   int stages;
   int tmem_cols;
+  int cg;                // 1: one CTA per tile;  2: CTA pair (cluster of 2, tcgen05 cta_group::2): a 256-pixel x BN tile,
+                         //    each CTA stages its own 128 pixels of A and HALF of the weight tile (halves the smem traffic of B)
+  int msub;              // 128-pixel sub-tiles per CTA (1 or 2): two sub-tiles share every weight tile (fewer operand bytes per MMA)
   // epilogue
   const float* bias;                 // [Cout] fp32 or nullptr
   const __half* residual;            // optional, same pixel grid as the output
@@ -69,13 +73,17 @@ struct ConvParams {
 
 #ifdef __CUDACC__
 
+// kCG = 1: one CTA per tile (no cluster);  kCG = 2: CTA pair, launched with cluster dimension 2.  Two instantiations
+// because a kernel that contains cta_group::2 instructions must be launched as a cluster.
+template <int kCG>
 __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16 KB | B BN*128 B] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_bytes = kConvBM * kConvBK * 2;
-  const int b_bytes = p.BN * kConvBK * 2;
-  const int stage_bytes = a_bytes + b_bytes;
+  const int a_bytes = kConvBM * kConvBK * 2;                 // one sub-tile of A
+  const int b_rows = kCG == 2 ? p.BN / 2 : p.BN;             // weight rows staged by THIS CTA
+  const int b_bytes = b_rows * kConvBK * 2;
+  const int stage_bytes = p.msub * a_bytes + b_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
@@ -91,14 +99,18 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
     dbg[0] = global_timer_ns(); dbg[7] = smid;
   }
 
-  // tile coordinates
-  const int n_tile = blockIdx.x % p.n_tiles;
-  int mt = blockIdx.x / p.n_tiles;
-  const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-  const int th = mt % p.tiles_h; mt /= p.tiles_h;
-  const int tn = mt;
-  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+  // tile coordinates: CTA -> (channel tile, msub consecutive 128-pixel tiles)
+  const uint32_t rank = kCG == 2 ? cluster_ctarank() : 0;    // leader = rank 0
+  const int unit = kCG == 2 ? (blockIdx.x >> 1) : blockIdx.x; // work unit: a CTA, or a CTA pair
+  const int n_tile = unit % p.n_tiles;
+  const int mt0 = kCG == 2 ? (unit / p.n_tiles) * 2 + (int)rank : (unit / p.n_tiles) * p.msub;
   const int num_kb = p.num_taps * p.kchunks;
+  auto tile_origin = [&](int sub, int& tw_, int& th_, int& w0_, int& h0_, int& n0_) {
+    int mt = mt0 + sub;
+    tw_ = mt % p.tiles_w; mt /= p.tiles_w;
+    th_ = mt % p.tiles_h; mt /= p.tiles_h;
+    w0_ = tw_ * p.bw; h0_ = th_ * p.bh; n0_ = mt * p.bn;
+  };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kMaxSrc; ++s) tma_prefetch_desc(&p.tmA[s]);
@@ -114,11 +126,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc_dyn(tmem_slot, (uint32_t)p.tmem_cols);
-    tmem_relinquish();
+    if constexpr (kCG == 2) { tmem_alloc_dyn_cg2(tmem_slot, (uint32_t)p.tmem_cols); tmem_relinquish_cg2(); }
+    else { tmem_alloc_dyn(tmem_slot, (uint32_t)p.tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();     // peer barriers must be initialised before remote arrivals
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
@@ -131,22 +143,34 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int tws[2], ths[2], w0s[2], h0s[2], n0s[2];
+      for (int sub = 0; sub < p.msub; ++sub) tile_origin(sub, tws[sub], ths[sub], w0s[sub], h0s[sub], n0s[sub]);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int tap = kb / p.kchunks;
         const int kc = kb - tap * p.kchunks;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-        tma_load_4d(sa, &p.tmA[p.tap_src[tap]], &full_bar[stage], kc * kConvBK, w0 + p.tap_dw[tap],
-                    h0 + p.tap_dh[tap], n0);
-        tma_load_2d(sb, &p.tmB, &full_bar[stage], tap * p.w_tap_stride + kc * kConvBK, n_tile * p.BN);
+        uint8_t* sb = sa + p.msub * a_bytes;
+        if constexpr (kCG == 2) {
+          // both CTAs' loads complete on the LEADER's full barrier; only the leader arms it (with the bytes of both)
+          const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
+          tma_load_4d_cg2(sa, &p.tmA[p.tap_src[tap]], lead_bar, kc * kConvBK, w0s[0] + p.tap_dw[tap],
+                          h0s[0] + p.tap_dh[tap], n0s[0]);
+          tma_load_2d_cg2(sb, &p.tmB, lead_bar, tap * p.w_tap_stride + kc * kConvBK, n_tile * p.BN + (int)rank * b_rows);
+        } else {
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          for (int sub = 0; sub < p.msub; ++sub)
+            tma_load_4d(sa + sub * a_bytes, &p.tmA[p.tap_src[tap]], &full_bar[stage], kc * kConvBK,
+                        w0s[sub] + p.tap_dw[tap], h0s[sub] + p.tap_dh[tap], n0s[sub]);
+          tma_load_2d(sb, &p.tmB, &full_bar[stage], tap * p.w_tap_stride + kc * kConvBK, n_tile * p.BN);
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_f16(kConvBM, p.BN);
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only in pair mode) =====================
+    const uint32_t idesc = umma_idesc_f16(kCG == 2 ? 2 * kConvBM : kConvBM, p.BN);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
@@ -155,229 +179,116 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
       if (dbg && lane == 0 && kb == 0) dbg[2] = global_timer_ns();
       if (lane == 0) {
         const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint64_t adesc = umma_desc_sw128(sa);
-        const uint64_t bdesc = umma_desc_sw128(sa + a_bytes);
+        const uint64_t bdesc = umma_desc_sw128(sa + p.msub * a_bytes);
+        if constexpr (kCG == 2) {
+          const uint64_t adesc = umma_desc_sw128(sa);
 #pragma unroll
-        for (int k = 0; k < kConvBK / 16; ++k) {
-          // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kConvBK / 16; ++k)
+            umma_f16_cg2(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_cg2(&empty_bar[stage], 3);                    // frees the stage in BOTH CTAs
+          if (kb == num_kb - 1) umma_commit_cg2(tmem_full_bar, 3);  // accumulators of both CTAs complete
+        } else {
+          for (int sub = 0; sub < p.msub; ++sub) {
+            const uint64_t adesc = umma_desc_sw128(sa + sub * a_bytes);
+#pragma unroll
+            for (int k = 0; k < kConvBK / 16; ++k) {
+              // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+              umma_f16(tmem_base + sub * p.BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);                 // frees this smem stage when the MMAs retire
+          if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulator complete
         }
-        umma_commit(&empty_bar[stage]);                 // frees this smem stage when the MMAs retire
-        if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulator complete
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
     if (dbg && lane == 0) dbg[3] = global_timer_ns();
-  } else {
-    // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
-    const int quad = warp & 3;                       // warps 2,3,4,5 -> quadrants 2,3,0,1
-    const int r = quad * 32 + lane;                  // row of the tile == TMEM lane
+  } else if (warp >= 2) {
+    // ===================== epilogue (8 warps: lane quadrant = warp % 4, column parity = (warp - 2) / 4) ==========
+    const int quad = warp & 3;                       // warps 2..9 -> quadrants 2,3,0,1,2,3,0,1
+    const int cpar = (warp - 2) >> 2;                // which half of the 16-column chunks this warp handles
+    const int r = quad * 32 + lane;                  // row of a sub-tile == TMEM lane
     const int lw = r % p.bw;
     const int lh = (r / p.bw) % p.bh;
     const int ln = r / (p.bw * p.bh);
-    const int w = w0 + lw, h = h0 + lh, n = n0 + ln;
-    const bool row_ok = (w < p.Wout) && (h < p.Hout) && (n < p.Nimg);
     const int col0 = n_tile * p.BN;
+    const int etid = threadIdx.x - 64;               // 0..255 among epilogue threads
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (dbg && threadIdx.x == 64) dbg[4] = global_timer_ns();
 
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-
     if (p.tma_out) {
       // ---------- staged epilogue ----------
-      // All operand stages are free now (every MMA that read them has retired), so the pipeline smem is reused:
-      //   [block b] 128 rows x 128 B (64 fp16 columns), SWIZZLE_128B — first the residual tile (TMA load), then the
-      //   finished outputs written in place, then one TMA store per block;  after the blocks: per-warp GN partials.
+      // All operand stages are free now (every MMA that read them has retired), so the pipeline smem is reused.
+      // Per sub-tile: BN/bc blocks of [128 rows x bc columns] fp16, swizzled like the TMA box — first the residual
+      // tile lands there (TMA load), then the finished outputs are written in place, then one TMA store per block.
+      // After the blocks of all sub-tiles: per-warp GroupNorm partials [msub][4 quads][BN][2].
       const int bc = p.epi_bc;                       // columns per staging block
       const int nblk = p.BN / bc;
       const int blk_bytes = kConvBM * bc * 2;
+      const int sub_bytes = nblk * blk_bytes;
       const int bshift = (bc == 64) ? 6 : (bc == 32 ? 5 : 4);
       // Swizzle<B,4,3>: the 16-byte unit index is XORed with address bits [7, 7+B); row pitch is 2*bc bytes
       const int swz = (bc == 64) ? (r & 7) : (bc == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
-      uint8_t* sblk = smem;
-      float* wsum = reinterpret_cast<float*>(smem + (size_t)nblk * blk_bytes);         // [4 quads][BN][2]
-      const int etid = threadIdx.x - 64;                                              // 0..127 among epilogue threads
+      float* wsum_all = reinterpret_cast<float*>(smem + (size_t)p.msub * sub_bytes);
       if (p.tma_res) {
         if (etid == 0) {
-          mbar_arrive_expect_tx(res_bar, (uint32_t)(nblk * blk_bytes));
-          for (int b = 0; b < nblk; ++b)
-            tma_load_4d(sblk + (size_t)b * blk_bytes, &p.tmRes, res_bar, col0 + b * bc, w0, h0, n0);
+          mbar_arrive_expect_tx(res_bar, (uint32_t)(p.msub * sub_bytes));
+          for (int sub = 0; sub < p.msub; ++sub) {
+            int tw, th, w0, h0, n0;
+            tile_origin(sub, tw, th, w0, h0, n0);
+            for (int b = 0; b < nblk; ++b)
+              tma_load_4d(smem + (size_t)sub * sub_bytes + (size_t)b * blk_bytes, &p.tmRes, res_bar, col0 + b * bc, w0, h0, n0);
+          }
         }
         mbar_wait(res_bar, 0);
       }
       const bool want_stats = p.gn_part[0] != nullptr;
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(trow + c, v);
-        tmem_ld_wait();
-        const int col = col0 + c;
-        float f[16];
+      for (int sub = 0; sub < p.msub; ++sub) {
+        int tw, th, w0, h0, n0;
+        tile_origin(sub, tw, th, w0, h0, n0);
+        const bool row_ok = (w0 + lw < p.Wout) && (h0 + lh < p.Hout) && (n0 + ln < p.Nimg);
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + sub * p.BN;
+        uint8_t* sblk = smem + (size_t)sub * sub_bytes;
+        float* wsum = wsum_all + (size_t)sub * 4 * p.BN * 2;                           // [4 quads][BN][2]
+        for (int c = cpar * 16; c < p.BN; c += 32) {
+          uint32_t v[16];
+          tmem_ld16(trow + c, v);
+          tmem_ld_wait();
+          const int col = col0 + c;
+          float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] += (col + j < p.Cout) ? __ldg(p.bias + col + j) : 0.f;
-        }
-        if (p.act == ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = gelu_erf_f(f[j]);
-        } else if (p.act == ACT_SILU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
-        }
-        // this thread's two 16-byte units inside the swizzled block
-        uint8_t* brow = sblk + (size_t)(c >> bshift) * blk_bytes + r * (2 * bc);
-        const int u0 = (c & (bc - 1)) >> 3;                  // 16-byte unit index of columns c..c+7 inside the block
-        uint4* a0 = reinterpret_cast<uint4*>(brow + (((u0) ^ swz) << 4));
-        uint4* a1 = reinterpret_cast<uint4*>(brow + (((u0 + 1) ^ swz) << 4));
-        if (p.tma_res) {
-          const uint4 r0 = *a0, r1 = *a1;
-          const __half2* h0p = reinterpret_cast<const __half2*>(&r0);
-          const __half2* h1p = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 x0 = __half22float2(h0p[j]);
-            const float2 x1 = __half22float2(h1p[j]);
-            f[2 * j] += x0.x; f[2 * j + 1] += x0.y;
-            f[8 + 2 * j] += x1.x; f[8 + 2 * j + 1] += x1.y;
+            for (int j = 0; j < 16; ++j) f[j] += (col + j < p.Cout) ? __ldg(p.bias + col + j) : 0.f;
           }
-        }
-        uint4 o0, o1;
-        __half2* q0 = reinterpret_cast<__half2*>(&o0);
-        __half2* q1 = reinterpret_cast<__half2*>(&o1);
+          if (p.act == ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          q0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-          q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
-        }
-        *a0 = o0; *a1 = o1;
-        if (want_stats) {
-          // statistics of the values as stored (fp16-rounded), zero for rows / columns outside the tensor
-          float sv[16], sq[16];
+            for (int j = 0; j < 16; ++j) f[j] = gelu_erf_f(f[j]);
+          } else if (p.act == ACT_SILU) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 x0 = __half22float2(q0[j]);
-            const float2 x1 = __half22float2(q1[j]);
-            sv[2 * j] = x0.x; sv[2 * j + 1] = x0.y; sv[8 + 2 * j] = x1.x; sv[8 + 2 * j + 1] = x1.y;
+            for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
           }
+          // this thread's two 16-byte units inside the swizzled block
+          uint8_t* brow = sblk + (size_t)(c >> bshift) * blk_bytes + r * (2 * bc);
+          const int u0 = (c & (bc - 1)) >> 3;                  // 16-byte unit index of columns c..c+7 inside the block
+          uint4* a0 = reinterpret_cast<uint4*>(brow + (((u0) ^ swz) << 4));
+          uint4* a1 = reinterpret_cast<uint4*>(brow + (((u0 + 1) ^ swz) << 4));
+          if (p.tma_res) {
+            const uint4 r0 = *a0, r1 = *a1;
+            const __half2* h0p = reinterpret_cast<const __half2*>(&r0);
+            const __half2* h1p = reinterpret_cast<const __half2*>(&r1);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (!row_ok || col + j >= p.Cout) sv[j] = 0.f;
-            sq[j] = sv[j] * sv[j];
-          }
-          // transpose-reduce over the 32 rows of this warp: 16 shuffles per moment
-#pragma unroll
-          for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-            const bool upper = (lane & bit) != 0;
-#pragma unroll
-            for (int j = 0; j < half; ++j) {
-              const float send_s = upper ? sv[j] : sv[j + half];
-              const float keep_s = upper ? sv[j + half] : sv[j];
-              sv[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
-              const float send_q = upper ? sq[j] : sq[j + half];
-              const float keep_q = upper ? sq[j + half] : sq[j];
-              sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+            for (int j = 0; j < 4; ++j) {
+              const float2 x0 = __half22float2(h0p[j]);
+              const float2 x1 = __half22float2(h1p[j]);
+              f[2 * j] += x0.x; f[2 * j + 1] += x0.y;
+              f[8 + 2 * j] += x1.x; f[8 + 2 * j + 1] += x1.y;
             }
           }
-          sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
-          sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
-          if ((lane & 1) == 0) {
-            const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            wsum[((size_t)quad * p.BN + c + cidx) * 2] = sv[0];
-            wsum[((size_t)quad * p.BN + c + cidx) * 2 + 1] = sq[0];
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (etid == 0) {
-        for (int b = 0; b < nblk; ++b)
-          if (col0 + b * bc < p.Cout) tma_store_4d(&p.tmOut, sblk + (size_t)b * blk_bytes, col0 + b * bc, w0, h0, n0);
-        tma_store_commit();
-      }
-      if (want_stats) {
-        const int slot = th * p.tiles_w + tw;
-        for (int cc = etid; cc < p.BN; cc += 128) {
-          if (col0 + cc >= p.Cout) continue;
-          const float s0 = wsum[((size_t)0 * p.BN + cc) * 2], q0s = wsum[((size_t)0 * p.BN + cc) * 2 + 1];
-          const float s1 = wsum[((size_t)1 * p.BN + cc) * 2], q1s = wsum[((size_t)1 * p.BN + cc) * 2 + 1];
-          const float s2 = wsum[((size_t)2 * p.BN + cc) * 2], q2s = wsum[((size_t)2 * p.BN + cc) * 2 + 1];
-          const float s3 = wsum[((size_t)3 * p.BN + cc) * 2], q3s = wsum[((size_t)3 * p.BN + cc) * 2 + 1];
-#pragma unroll
-          for (int d = 0; d < 2; ++d) {
-            float* part = p.gn_part[d];
-            if (!part) continue;
-            const size_t ch = (size_t)p.gn_coff[d] + col0 + cc;
-            if (p.bn == 1) {
-              float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
-              dst[0] = (s0 + s1) + (s2 + s3);
-              dst[1] = (q0s + q1s) + (q2s + q3s);
-            } else {   // two images per tile: rows 0..63 -> n0, rows 64..127 -> n0 + 1
-              float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
-              dst[0] = s0 + s1; dst[1] = q0s + q1s;
-              if (n0 + 1 < p.Nimg) {
-                float* dst1 = part + (((size_t)(n0 + 1) * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
-                dst1[0] = s2 + s3; dst1[1] = q2s + q3s;
-              }
-            }
-          }
-        }
-      }
-      if (etid == 0) tma_store_wait_all();
-    } else {
-      // ---------- direct epilogue (fp32 NCHW model head, or RS_CONV_EPI=direct) ----------
-    __half* orow = p.out ? p.out + n * p.out_sN + h * p.out_sH + w * p.out_sW : nullptr;
-    const __half* rrow = p.residual ? p.residual + n * p.res_sN + h * p.res_sH + w * p.res_sW : nullptr;
-
-    for (int c = 0; c < p.BN; c += 16) {
-      uint32_t v[16];
-      __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the divergent tail of the last chunk
-      tmem_ld16(trow + c, v);
-      tmem_ld_wait();
-      const int col = col0 + c;
-      if (!row_ok || col >= p.Cout) continue;
-      float f[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-      const bool full = (col + 16 <= p.Cout);
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (full || col + j < p.Cout) f[j] += __ldg(p.bias + col + j);
-      }
-      if (p.act == ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = gelu_erf_f(f[j]);
-      } else if (p.act == ACT_SILU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
-      }
-      if (rrow) {
-        if (full) {
-          const uint4 r0 = *reinterpret_cast<const uint4*>(rrow + col);
-          const uint4 r1 = *reinterpret_cast<const uint4*>(rrow + col + 8);
-          const __half2* h0p = reinterpret_cast<const __half2*>(&r0);
-          const __half2* h1p = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 a = __half22float2(h0p[j]);
-            const float2 b = __half22float2(h1p[j]);
-            f[2 * j] += a.x; f[2 * j + 1] += a.y;
-            f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
-          }
-        } else {
-          for (int j = 0; j < 16 && col + j < p.Cout; ++j) f[j] += __half2float(rrow[col + j]);
-        }
-      }
-      if (p.out_f32_nchw) {
-        for (int j = 0; j < 16 && col + j < p.Cout; ++j)
-          p.out_f32_nchw[(((long long)n * p.Cout + (col + j)) * p.Hout + h) * p.Wout + w] = f[j];
-      }
-      if (orow) {
-        if (full) {
           uint4 o0, o1;
           __half2* q0 = reinterpret_cast<__half2*>(&o0);
           __half2* q1 = reinterpret_cast<__half2*>(&o1);
@@ -386,23 +297,145 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
             q0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
             q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
           }
-          *reinterpret_cast<uint4*>(orow + col) = o0;
-          *reinterpret_cast<uint4*>(orow + col + 8) = o1;
-        } else {
-          for (int j = 0; j < 16 && col + j < p.Cout; ++j) orow[col + j] = __float2half_rn(f[j]);
+          *a0 = o0; *a1 = o1;
+          if (want_stats) {
+            // statistics of the values as stored (fp16-rounded), zero for rows / columns outside the tensor
+            float sv[16], sq[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 x0 = __half22float2(q0[j]);
+              const float2 x1 = __half22float2(q1[j]);
+              sv[2 * j] = x0.x; sv[2 * j + 1] = x0.y; sv[8 + 2 * j] = x1.x; sv[8 + 2 * j + 1] = x1.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (!row_ok || col + j >= p.Cout) sv[j] = 0.f;
+              sq[j] = sv[j] * sv[j];
+            }
+            // transpose-reduce over the 32 rows of this warp: 16 shuffles per moment
+#pragma unroll
+            for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+              const bool upper = (lane & bit) != 0;
+#pragma unroll
+              for (int j = 0; j < half; ++j) {
+                const float send_s = upper ? sv[j] : sv[j + half];
+                const float keep_s = upper ? sv[j + half] : sv[j];
+                sv[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+                const float send_q = upper ? sq[j] : sq[j + half];
+                const float keep_q = upper ? sq[j + half] : sq[j];
+                sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+              }
+            }
+            sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+            sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
+            if ((lane & 1) == 0) {
+              const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              wsum[((size_t)quad * p.BN + c + cidx) * 2] = sv[0];
+              wsum[((size_t)quad * p.BN + c + cidx) * 2 + 1] = sq[0];
+            }
+          }
         }
       }
-    }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 32 * kConvEpiWarps);
+      if (etid == 0) {
+        for (int sub = 0; sub < p.msub; ++sub) {
+          int tw, th, w0, h0, n0;
+          tile_origin(sub, tw, th, w0, h0, n0);
+          for (int b = 0; b < nblk; ++b)
+            if (col0 + b * bc < p.Cout)
+              tma_store_4d(&p.tmOut, smem + (size_t)sub * sub_bytes + (size_t)b * blk_bytes, col0 + b * bc, w0, h0, n0);
+        }
+        tma_store_commit();
+      }
+      if (want_stats) {
+        for (int sub = 0; sub < p.msub; ++sub) {
+          int tw, th, w0, h0, n0;
+          tile_origin(sub, tw, th, w0, h0, n0);
+          if (n0 >= p.Nimg) continue;                  // padding tile of an odd pair
+          const float* wsum = wsum_all + (size_t)sub * 4 * p.BN * 2;
+          const int slot = th * p.tiles_w + tw;
+          for (int cc = etid; cc < p.BN; cc += 32 * kConvEpiWarps) {
+            if (col0 + cc >= p.Cout) continue;
+            const float s0 = wsum[((size_t)0 * p.BN + cc) * 2], q0s = wsum[((size_t)0 * p.BN + cc) * 2 + 1];
+            const float s1 = wsum[((size_t)1 * p.BN + cc) * 2], q1s = wsum[((size_t)1 * p.BN + cc) * 2 + 1];
+            const float s2 = wsum[((size_t)2 * p.BN + cc) * 2], q2s = wsum[((size_t)2 * p.BN + cc) * 2 + 1];
+            const float s3 = wsum[((size_t)3 * p.BN + cc) * 2], q3s = wsum[((size_t)3 * p.BN + cc) * 2 + 1];
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+              float* part = p.gn_part[d];
+              if (!part) continue;
+              const size_t ch = (size_t)p.gn_coff[d] + col0 + cc;
+              if (p.bn == 1) {
+                float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
+                dst[0] = (s0 + s1) + (s2 + s3);
+                dst[1] = (q0s + q1s) + (q2s + q3s);
+              } else {   // two images per tile: rows 0..63 -> n0, rows 64..127 -> n0 + 1
+                float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
+                dst[0] = s0 + s1; dst[1] = q0s + q1s;
+                if (n0 + 1 < p.Nimg) {
+                  float* dst1 = part + (((size_t)(n0 + 1) * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
+                  dst1[0] = s2 + s3; dst1[1] = q2s + q3s;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (etid == 0) tma_store_wait_all();
+    } else {
+      // ---------- direct epilogue (fp32 NCHW model head, or RS_CONV_EPI=direct) ----------
+      for (int sub = 0; sub < p.msub; ++sub) {
+        int tw, th, w0, h0, n0;
+        tile_origin(sub, tw, th, w0, h0, n0);
+        const int w = w0 + lw, h = h0 + lh, n = n0 + ln;
+        const bool row_ok = (w < p.Wout) && (h < p.Hout) && (n < p.Nimg);
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + sub * p.BN;
+        __half* orow = p.out ? p.out + n * p.out_sN + h * p.out_sH + w * p.out_sW : nullptr;
+        const __half* rrow = p.residual ? p.residual + n * p.res_sN + h * p.res_sH + w * p.res_sW : nullptr;
+        for (int c = cpar * 16; c < p.BN; c += 32) {
+          uint32_t v[16];
+          __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the divergent tail of the last chunk
+          tmem_ld16(trow + c, v);
+          tmem_ld_wait();
+          const int col = col0 + c;
+          if (!row_ok || col >= p.Cout) continue;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col + j < p.Cout) f[j] += __ldg(p.bias + col + j);
+          }
+          if (p.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = gelu_erf_f(f[j]);
+          } else if (p.act == ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = silu_f(f[j]);
+          }
+          if (rrow)
+            for (int j = 0; j < 16 && col + j < p.Cout; ++j) f[j] += __half2float(rrow[col + j]);
+          if (p.out_f32_nchw)
+            for (int j = 0; j < 16 && col + j < p.Cout; ++j)
+              p.out_f32_nchw[(((long long)n * p.Cout + (col + j)) * p.Hout + h) * p.Wout + w] = f[j];
+          if (orow)
+            for (int j = 0; j < 16 && col + j < p.Cout; ++j) orow[col + j] = __float2half_rn(f[j]);
+        }
+      }
     }
   }
 
   // teardown: everyone done with TMEM before the allocating warp frees it
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();    // pair: neither CTA may retire while the other can still
+                                                               // touch its smem / barriers / TMEM
   if (dbg && threadIdx.x == 0) dbg[5] = global_timer_ns();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_dyn(tmem_base, (uint32_t)p.tmem_cols);
+    if constexpr (kCG == 2) tmem_dealloc_dyn_cg2(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc_dyn(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 

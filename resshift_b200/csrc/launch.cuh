@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <utility>
 #include <vector>
@@ -92,16 +93,30 @@ inline bool env_is(const char* name, const char* val) {
 // attribute (PDL), so kernel N+1's prologue overlaps kernel N's tail, also inside captured graphs.
 // RS_PDL=0 turns the attribute off.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                            Args&&... args) {
+inline cudaError_t launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                             int cluster_x, Args&&... args) {
   static const int use_pdl = env_int("RS_PDL", 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (use_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  return launch_kc(kernel, grid, block, smem, st, 1, std::forward<Args>(args)...);
 }
 
 inline int pow2_floor_div(int x, int cap) {   // largest power of two dividing x, capped
@@ -135,6 +150,53 @@ struct ConvDesc {
   int grid = 0; size_t smem = 0;
 };
 
+struct TileConfig { int BN = 0, msub = 1, stages = 2, occ = 1, cg = 1; double est_cycles = 1e30; };
+
+// Cost model calibrated on B200 timelines (profiles/r1_s5_*, r1_s6_*).  Per 64-channel k-block and 128-pixel tile the
+// tensor pipe needs 2*BN cycles; every operand byte crosses shared memory twice (TMA write + UMMA read, 128 B/clk
+// per SM), which is what actually bounds a single-CTA tile (A 16 KB + B BN*128 B);  a CTA pair (cg = 2,
+// tcgen05 cta_group::2) stages only half of B per SM.  Shallow rings are additionally latency-bound (~3000 cycles
+// per load).  The epilogue (~18 cycles per column + set-up) hides under a co-resident CTA; whole waves are counted.
+inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn) {
+  const int f_msub = env_int("RS_CONV_MSUB", 0), f_occ = env_int("RS_CONV_OCC", 0), f_stages = env_int("RS_CONV_STAGES", 0);
+  const int f_cg = env_int("RS_CONV_CG", 0);
+  TileConfig best;
+  for (int cand = std::min(cout16, 256); cand >= 16; cand -= 16) {
+    if (f_bn ? (cand != std::min(f_bn, std::min(cout16, 256))) : (cout16 % cand != 0)) continue;
+    const int n_tiles = (cout16 + cand - 1) / cand;
+    for (int cg = 1; cg <= 2; ++cg) {
+      if (f_cg && cg != f_cg && !(f_cg == 2 && m_tiles < 2)) continue;   // a single tile cannot form a pair
+      if (cg == 2 && (cand % 16 != 0 || m_tiles < 2)) continue;
+      for (int ms = 1; ms <= 2; ++ms) {
+        if (ms == 2 && (f_msub != 2 || cg == 2 || m_tiles % 2 || 2 * cand > 512)) continue;   // msub = 2 only on request
+        const int sbytes = ms * kConvBM * kConvBK * 2 + (cand / cg) * kConvBK * 2;
+        for (int occ = 1; occ <= 2; ++occ) {
+          if (f_occ && occ != f_occ) continue;
+          if (occ == 2 && ms * cand > 256) continue;                       // TMEM: 512 columns per SM
+          const int budget = (occ == 2 ? 111 : 222) * 1024 - 2048;
+          int st = std::min(std::min(8, std::max(2, num_kb)), budget / sbytes);
+          if (f_stages) st = f_stages;
+          if (st < 2 || (size_t)st * sbytes + 1280 > (size_t)(occ == 2 ? 113 : 227) * 1024) continue;
+          const double smem_cycles = (sbytes + ms * (kConvBM * kConvBK * 2.0 + (cand / cg) * kConvBK * 2.0)) / 128.0;
+          // SM time for every resident CTA to advance one k-block: tensor / smem work of each, or the load latency
+          // amortised over the ring depth
+          const double kb_cycles = std::max(occ * std::max(ms * 2.0 * cand, smem_cycles), 3000.0 / st);
+          const double epi = 18.0 * cand * ms + 3000.0 + (cg == 2 ? 2500.0 : 0.0);  // + pipeline fill / set-up (+ cluster syncs)
+          const long long units = (long long)((m_tiles + cg * ms - 1) / (cg * ms)) * n_tiles;   // CTAs or CTA pairs
+          const double slots = (cg == 2 ? 74.0 : 148.0) * occ;
+          const double waves = std::ceil((double)units / slots);
+          const double round = num_kb * kb_cycles + (occ == 2 ? 0.5 * epi : epi);
+          const double total = waves * round;
+          if (total < best.est_cycles) {
+            best.est_cycles = total; best.BN = cand; best.msub = ms; best.stages = st; best.occ = occ; best.cg = cg;
+          }
+        }
+      }
+    }
+  }
+  return best;
+}
+
 inline int conv_finalize(ConvDesc& d) {
   ConvParams& p = d.prm;
   std::memset(&p, 0, sizeof(p));
@@ -153,39 +215,26 @@ inline int conv_finalize(ConvDesc& d) {
   p.bn = kConvBM / (p.bw * p.bh);
   p.tiles_w = Wout / p.bw; p.tiles_h = Hout / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  // channel tile
+  // ---- tile configuration: channel tile BN, sub-tiles per CTA (msub), CTAs per SM (occ), ring depth (stages) ----
+  // Chosen by a small cost model calibrated on B200 timelines (profiles/r1_s5_*): the main loop is bound by the bytes
+  // of TMA loads in flight per SM (ring capacity / ~3000-cycle load latency, at most ~75 B/clk) unless the tensor
+  // pipe is slower (2*BN cycles per 64-channel k-block per 128-pixel sub-tile); the epilogue (~18 cycles per output
+  // column per sub-tile) hides under the other resident CTA when two fit; whole waves of CTAs are counted.
   const int cout16 = (d.Cout + 15) / 16 * 16;
-  int BN = 0;
-  const int forced = d.bn_override ? d.bn_override : env_int("RS_CONV_BN", 0);
-  if (forced) {
-    BN = std::min(forced, std::min(cout16, 256));
-  } else {
-    int smallest = 0;
-    for (int cand = std::min(cout16, 256); cand >= 16; cand -= 16) {
-      if (cout16 % cand) continue;
-      smallest = cand;
-      if (!BN && (long long)m_tiles * (cout16 / cand) >= 120) BN = cand;
-      if (cand <= 32) break;
-    }
-    if (!BN) BN = smallest;
-  }
-  RS_CHECK(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid BN");
+  const int num_kb = p.num_taps * p.kchunks;
+  const TileConfig tc = pick_tile_config(m_tiles, cout16, num_kb, d.bn_override ? d.bn_override : env_int("RS_CONV_BN", 0));
+  const int BN = tc.BN, msub = tc.msub, stages = tc.stages, cg = tc.cg;
+  p.cg = cg;
+  RS_CHECK(BN >= 16 && BN <= 256 && BN % 16 == 0, "no valid tile configuration");
   p.BN = BN; p.n_tiles = (cout16 + BN - 1) / BN;
-  int cols = 32; while (cols < BN) cols *= 2;
+  p.msub = msub;
+  int cols = 32; while (cols < msub * BN) cols *= 2;
   p.tmem_cols = cols;
-  const int stage_bytes = kConvBM * kConvBK * 2 + BN * kConvBK * 2;
-  int occ = env_int("RS_CONV_OCC", 2);
-  int stages = env_int("RS_CONV_STAGES", 0);
-  if (!stages) {
-    int budget = (occ >= 2 ? 110 : 220) * 1024 - 2048;
-    stages = budget / stage_bytes;
-    if (stages < 3) stages = (220 * 1024 - 2048) / stage_bytes;
-    stages = std::max(2, std::min(stages, 8));
-  }
+  const int stage_bytes = msub * kConvBM * kConvBK * 2 + (BN / cg) * kConvBK * 2;
   p.stages = stages;
   d.smem = (size_t)stages * stage_bytes + 1024 + 256;
   RS_CHECK(d.smem <= 227 * 1024, "shared memory budget exceeded");
-  d.grid = m_tiles * p.n_tiles;
+  d.grid = cg == 2 ? ((m_tiles + 1) / 2) * p.n_tiles * 2 : (m_tiles / msub) * p.n_tiles;
   // taps
   if (d.stride == 1) {
     int t = 0;
@@ -226,7 +275,7 @@ inline int conv_finalize(ConvDesc& d) {
       if (rc) return rc;
     }
     // the staging area (column blocks + per-warp GN partials) must fit in the operand ring
-    const size_t need = (size_t)BN * kConvBM * 2 + (size_t)4 * BN * 2 * sizeof(float);
+    const size_t need = (size_t)msub * ((size_t)BN * kConvBM * 2 + (size_t)4 * BN * 2 * sizeof(float));
     RS_CHECK(need <= (size_t)stages * stage_bytes, "epilogue staging does not fit in the pipeline shared memory");
   }
   p.gn_slots = p.tiles_w * p.tiles_h;
@@ -255,7 +304,7 @@ inline int conv_finalize(ConvDesc& d) {
     }
   }
   if (!env_is("RS_CONV_IMPL", "simt")) {
-    int rc = encode_weight_map(&p.tmB, d.wt, p.num_taps * d.ipad, d.Cout, BN);
+    int rc = encode_weight_map(&p.tmB, d.wt, p.num_taps * d.ipad, d.Cout, BN / cg);
     if (rc) return rc;
   }
   return 0;
@@ -264,7 +313,9 @@ inline int conv_finalize(ConvDesc& d) {
 inline int conv_init() {   // once per process, outside any stream capture
   static bool attr_set = false;
   if (!attr_set) {
-    RS_CUDA_OK(cudaFuncSetAttribute(conv_gemm_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RS_CUDA_OK(cudaFuncSetAttribute(conv_gemm_sm100_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RS_CUDA_OK(cudaFuncSetAttribute(conv_gemm_sm100_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RS_CUDA_OK(cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
   return 0;
@@ -276,7 +327,10 @@ inline int conv_launch(const ConvDesc& d, cudaStream_t st) {
     const int warps = 8;
     (void)launch_k(conv_simt_kernel, dim3((unsigned)((npix + warps - 1) / warps)), dim3(warps * 32), (size_t)(0), st, d.prm, d.simt);
   } else {
-    (void)launch_k(conv_gemm_sm100_kernel, dim3(d.grid), dim3(kConvThreads), (size_t)(d.smem), st, d.prm);
+    if (d.prm.cg == 2)
+      (void)launch_kc(conv_gemm_sm100_kernel<2>, dim3(d.grid), dim3(kConvThreads), (size_t)(d.smem), st, 2, d.prm);
+    else
+      (void)launch_kc(conv_gemm_sm100_kernel<1>, dim3(d.grid), dim3(kConvThreads), (size_t)(d.smem), st, 1, d.prm);
   }
   RS_CUDA_OK(cudaGetLastError());
   return 0;
@@ -324,20 +378,35 @@ inline int gn_launch(const GnDesc& g, cudaStream_t st) {
     (void)launch_k(gn_stats_kernel, dim3(chunks, N), dim3(256), (size_t)lanes * C * 2 * sizeof(float), st, sp);
     RS_CUDA_OK(cudaGetLastError());
   }
+  // apply: ~2 CTAs per SM in total (each CTA re-derives the per-channel affine from the partials, so fewer, fatter
+  // CTAs keep that prologue traffic small), at least 32 rows each
+  int actas = std::max(1, std::min((HW + 31) / 32, (148 * 2 + N - 1) / N));
+  const int arows = (HW + actas - 1) / actas;
+  actas = (HW + arows - 1) / arows;
   GnApplyParams ap{g.in.ptr, g.in.sN(), g.in.ld, g.out.ptr, g.out.sN(), g.out.ld, C, HW, N, g.part, slots,
-                   g.gamma, g.beta, g.film, g.film_sN, g.silu, rows, 1e-5f};
-  (void)launch_k(gn_apply_kernel, dim3(chunks, N), dim3(256), (size_t)(2 * C + 64) * sizeof(float), st, ap);
+                   g.gamma, g.beta, g.film, g.film_sN, g.silu, arows, 1e-5f};
+  (void)launch_k(gn_apply_kernel, dim3(actas, N), dim3(256), (size_t)(2 * C + 64) * sizeof(float), st, ap);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+inline size_t attn_smem_bytes(int E) {
+  return (size_t)2 * 3 * 64 * kAttnPad * 2 + (size_t)64 * (E + 8) * 2 + 64 * sizeof(int);
 }
 
 inline int attn_launch(const View& qkv, const View& out, const float* bias, int heads, int E, int shift,
                        cudaStream_t st) {
   RS_CHECK(qkv.H % 8 == 0 && qkv.W % 8 == 0, "window attention needs H, W multiples of 8");
-  RS_CHECK(E == heads * 32, "window attention kernel is specialised for head_dim 32");
-  WinAttnParams p{qkv.ptr, qkv.ld, out.ptr, out.ld, bias, qkv.N, qkv.H, qkv.W, heads, E, shift,
-                  0.17677669529663687f, env_is("RS_ATTN_IMPL", "simt") ? 1 : 0};
-  (void)launch_k(window_attn_kernel, dim3(dim3(qkv.N * (qkv.H / 8) * (qkv.W / 8), heads)), dim3(128), (size_t)(0), st, p);
+  RS_CHECK(E == heads * 32 && E % 8 == 0, "window attention kernel is specialised for head_dim 32");
+  WinAttnParams p{qkv.ptr, qkv.ld, out.ptr, out.ld, bias, qkv.N, qkv.H, qkv.W, heads, E, shift, 0.17677669529663687f};
+  const int windows = qkv.N * (qkv.H / 8) * (qkv.W / 8);
+  if (env_is("RS_ATTN_IMPL", "simt")) {
+    (void)launch_k(window_attn_simt_kernel, dim3(windows, heads), dim3(64), (size_t)0, st, p);
+  } else {
+    const size_t smem = attn_smem_bytes(E);
+    RS_CHECK(smem <= 160 * 1024, "attention tile does not fit in shared memory");   // limit raised in conv_init()
+    (void)launch_k(window_attn_kernel, dim3(windows), dim3(128), smem, st, p);
+  }
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -109,23 +109,31 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
   float* s_rstd = s_mean + 32;
   const int n = blockIdx.y;
   const int cpg = p.C / 32;
-  // group statistics: 8 threads per group walk (slot, channel-in-group) pairs in a fixed order
+  // per-channel totals over the slots (independent loads, fixed order), staged in s_a / s_b; then per-group
+  // mean / rstd in a fixed order over the group's channels
   {
-    const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
     const float* part = p.part + (size_t)n * p.slots * p.C * 2;
-    float s = 0.f, q = 0.f;
-    const int items = p.slots * cpg;
-    for (int it = sub; it < items; it += 8) {
-      const int slot = it / cpg, j = it - slot * cpg;
-      const float* e = part + ((size_t)slot * p.C + g * cpg + j) * 2;
-      s += e[0]; q += e[1];
-    }
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      float s = 0.f, q = 0.f;
+      int sl = 0;
+      for (; sl + 4 <= p.slots; sl += 4) {
+        float2 e[4];
 #pragma unroll
-    for (int off = 4; off; off >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, off);
-      q += __shfl_xor_sync(0xffffffffu, q, off);
+        for (int u = 0; u < 4; ++u) e[u] = *reinterpret_cast<const float2*>(part + ((size_t)(sl + u) * p.C + c) * 2);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { s += e[u].x; q += e[u].y; }
+      }
+      for (; sl < p.slots; ++sl) {
+        const float2 e = *reinterpret_cast<const float2*>(part + ((size_t)sl * p.C + c) * 2);
+        s += e.x; q += e.y;
+      }
+      s_a[c] = s; s_b[c] = q;
     }
-    if (sub == 0) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int g = threadIdx.x;
+      float s = 0.f, q = 0.f;
+      for (int j = 0; j < cpg; ++j) { s += s_a[g * cpg + j]; q += s_b[g * cpg + j]; }
       const float inv_cnt = 1.0f / (float)((long long)cpg * p.HW);
       const float mean = s * inv_cnt;
       const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);

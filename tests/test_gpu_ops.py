@@ -36,11 +36,18 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+@pytest.mark.parametrize("impl", ["tcgen05_cg1", "tcgen05_cg2", "tcgen05_msub2", "simt"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv2d(case, impl):
     N, H, W, Ci, Co, k, s, bn = case
-    os.environ["RS_CONV_IMPL"] = impl
+    os.environ["RS_CONV_IMPL"] = impl.split("_")[0]
+    if impl.endswith("msub2"):
+        os.environ["RS_CONV_MSUB"] = "2"       # two 128-pixel sub-tiles per CTA (falls back to 1 for odd tile counts)
+        os.environ["RS_CONV_CG"] = "1"
+    elif impl.endswith("cg1"):
+        os.environ["RS_CONV_CG"] = "1"         # one CTA per 128-pixel tile (tcgen05 cta_group::1)
+    elif impl.endswith("cg2"):
+        os.environ["RS_CONV_CG"] = "2"         # CTA pairs: 256-pixel tiles, tcgen05 cta_group::2, half of B per CTA
     try:
         g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000)
         x = G.nhwc16(torch.randn(N, Ci, H, W, device="cuda", generator=g))
@@ -55,6 +62,8 @@ def test_conv2d(case, impl):
         assert st["nan"] == 0 and st["max_abs"] <= _tol(ref), st
     finally:
         os.environ.pop("RS_CONV_IMPL", None)
+        os.environ.pop("RS_CONV_MSUB", None)
+        os.environ.pop("RS_CONV_CG", None)
 
 
 @pytest.mark.parametrize("act", [1, 2])
@@ -88,8 +97,9 @@ def test_conv2d_channel_slices():
     assert obuf[..., :320].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("msub", ["cg1", "cg1_msub2", "cg2"])
 @pytest.mark.parametrize("case", [(2, 64, 64, 64, 160, 3), (3, 16, 16, 160, 320, 3), (3, 8, 8, 320, 640, 1), (5, 8, 8, 64, 32, 3)])
-def test_conv2d_fused_groupnorm_statistics(case):
+def test_conv2d_fused_groupnorm_statistics(case, msub):
     """The conv epilogue's per-(image, tile slot, channel) partial sums must add up to the sums of the stored fp16
     output, written at a channel offset of a wider statistics buffer (concat consumers), and be bit-reproducible."""
     import ctypes as C
@@ -102,6 +112,8 @@ def test_conv2d_fused_groupnorm_statistics(case):
     wp, ipad = G.pack_weight(w)
     cstride, coff = Co + 32, 32
     outs, parts = [], []
+    os.environ["RS_CONV_MSUB"] = "2" if msub.endswith("msub2") else "1"
+    os.environ["RS_CONV_CG"] = "2" if msub == "cg2" else "1"
     for rep in range(2):
         out = torch.empty(N, H, W, Co, dtype=torch.float16, device="cuda")
         part = torch.full((N * 64 * cstride * 2,), float("nan"), dtype=torch.float32, device="cuda")
@@ -112,6 +124,8 @@ def test_conv2d_fused_groupnorm_statistics(case):
         torch.cuda.synchronize()
         outs.append(out)
         parts.append(part[:N * slots.value * cstride * 2].view(N, slots.value, cstride, 2)[:, :, coff:coff + Co].clone())
+    os.environ.pop("RS_CONV_MSUB", None)
+    os.environ.pop("RS_CONV_CG", None)
     assert torch.equal(outs[0], outs[1]) and torch.equal(parts[0], parts[1])         # deterministic
     ref = G.ref_conv(x, w, b, residual=res)
     assert (G.nchw32(outs[0]) - ref).abs().max().item() <= _tol(ref)
