@@ -140,6 +140,10 @@ long long rs_op_groupnorm_scratch_floats(int N, int H, int W, int C);
 int rs_op_expand_relpos(const float* table_225xh, float* dense_hx64x64, int heads, void* stream);
 int rs_op_window_attention(const void* qkv, int N, int H, int W, int heads, int shift, const float* bias_dense,
                            void* out, void* stream);
+/* fused Swin MLP (reference models/swin_transformer.py:17-33,279): out = residual + fc2(GELU(fc1(x))) */
+int rs_op_mlp(const void* x, int N, int H, int W, int E, int Hd, const void* w1_packed, const float* b1,
+              const void* w2_packed, const float* b2, const void* residual, void* out, void* dbg_timeline_or_null,
+              void* stream);
 /* host-only: tile configuration the conv launcher picks: out[5] = BN, msub, stages, CTAs/SM, estimated cycles */
 int rs_debug_tile_config(int m_tiles, int cout, int num_kblocks, int32_t* out);
 /* nearest x2 (reference models/unet.py:71-81) */

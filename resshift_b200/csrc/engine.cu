@@ -253,7 +253,7 @@ int build_inventory(rs_engine& e) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-enum OpKind { OP_CONV, OP_GN, OP_ATTN, OP_UPSAMPLE };
+enum OpKind { OP_CONV, OP_GN, OP_ATTN, OP_UPSAMPLE, OP_MLP };
 
 struct Tensor {
   size_t bytes = 0;
@@ -270,6 +270,9 @@ struct Op {
   View a_in, a_out; const float* a_bias = nullptr; int a_shift = 0;
   // upsample
   View u_in, u_out;
+  // fused MLP
+  MlpDesc mlp;
+  std::string w2_name, b2_name;
   std::string w_name, b_name, g_name;   // parameter names resolved at bind
   size_t stats_off = 0;                 // GroupNorm: offset of its partial-sum buffer inside the stats region
   bool to_f32 = false;                  // conv: writes the fp32 NCHW model output
@@ -326,6 +329,7 @@ struct Builder {
   size_t stats_off = 0;
   struct Writer { long long off; int C; int list; int op; };
   std::map<int, std::vector<Writer>> writers;      // tensor id -> latest conv writers by channel range
+  const bool fuse_mlp = env_int("RS_MLP_FUSE", 1) && !env_is("RS_CONV_IMPL", "simt");
   const bool fuse_stats = env_int("RS_GN_FUSE", 1) && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt");
   Builder(rs_plan& p) : P(p), E(*p.e), cur(&p.ops) {}
   int list_id() const { return cur == &P.fe_ops ? 0 : 1; }
@@ -388,6 +392,21 @@ struct Builder {
     P.touch(qkv, i); P.touch(out, i);
     cur->push_back(op);
   }
+  void mlp(const View& in, const std::string& name, int E, int Hd, const View& out, const View& res) {
+    Op op; op.kind = OP_MLP;
+    op.mlp.in = in; op.mlp.out = out; op.mlp.res = res; op.mlp.has_res = true; op.mlp.E = E; op.mlp.Hd = Hd;
+    op.w_name = name + ".fc1.weight"; op.b_name = name + ".fc1.bias";
+    op.w2_name = name + ".fc2.weight"; op.b2_name = name + ".fc2.bias";
+    const int i = opi();
+    P.touch(in, i); P.touch(out, i); P.touch(res, i);
+    cur->push_back(op);
+    if (out.tens >= 0) {
+      auto& ws = writers[out.tens];
+      ws.erase(std::remove_if(ws.begin(), ws.end(), [&](const Writer& w) {
+                 return w.off < out.off + E && out.off < w.off + w.C; }), ws.end());
+      ws.push_back({out.off, E, list_id(), (int)cur->size() - 1});
+    }
+  }
   void upsample(const View& in, const View& out) {
     Op op; op.kind = OP_UPSAMPLE; op.u_in = in; op.u_out = out;
     const int i = opi();
@@ -430,9 +449,13 @@ struct Builder {
       conv(a, b + ".attn.proj", 1, 1, Ed, &e, &e, ACT_NONE);              // x = shortcut + attn
       View n2 = P.make_view(x.N, x.H, x.W, Ed);
       gn(e, b + ".norm2", n2, 0, -1);
-      View f = P.make_view(x.N, x.H, x.W, hidden);
-      conv(n2, b + ".mlp.fc1", 1, 1, hidden, &f, nullptr, ACT_GELU);
-      conv(f, b + ".mlp.fc2", 1, 1, Ed, &e, &e, ACT_NONE);                // x = x + mlp
+      if (fuse_mlp && mlp_supported(Ed, hidden, x.H, x.W)) {
+        mlp(n2, b + ".mlp", Ed, hidden, e, e);                            // x = x + fc2(gelu(fc1(n2))), one kernel
+      } else {
+        View f = P.make_view(x.N, x.H, x.W, hidden);
+        conv(n2, b + ".mlp.fc1", 1, 1, hidden, &f, nullptr, ACT_GELU);
+        conv(f, b + ".mlp.fc2", 1, 1, Ed, &e, &e, ACT_NONE);              // x = x + mlp
+      }
     }
     conv(e, p + ".patch_unembed.proj", 1, 1, x.C, &out, nullptr, ACT_NONE);
     return 0;
@@ -640,6 +663,26 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       RS_CHECK(op.gn.gamma && op.gn.beta, "missing GroupNorm parameters " + op.g_name);
       op.gn.part = reinterpret_cast<float*>(P.ws + P.off_stats + op.stats_off);
       P.launches += op.gn.fused ? 1 : 2;
+    } else if (op.kind == OP_MLP) {
+      MlpDesc& m = op.mlp;
+      resolve(P, m.in); resolve(P, m.out); resolve(P, m.res);
+      m.w1 = E.at<__half>(op.w_name); m.b1 = E.at<float>(op.b_name);
+      m.w2 = E.at<__half>(op.w2_name); m.b2 = E.at<float>(op.b2_name);
+      RS_CHECK(m.w1 && m.w2 && m.b1 && m.b2, "missing MLP parameters " + op.w_name);
+      const Param* w1p = E.find(op.w_name); const Param* w2p = E.find(op.w2_name);
+      RS_CHECK(w1p->ipad == m.E && w2p->ipad == m.Hd, "MLP weight padding");
+      for (int i = 0; i < 2; ++i) {
+        m.gn_part[i] = nullptr;
+        if (i < (int)op.stat_dst.size()) {
+          const Op::StatDst& sd = op.stat_dst[i];
+          const Op& g = (sd.list == 0 ? P.fe_ops : P.ops)[sd.op];
+          m.gn_part[i] = reinterpret_cast<float*>(P.ws + P.off_stats + g.stats_off);
+          m.gn_cstride[i] = g.gn.in.C;
+          m.gn_coff[i] = sd.coff;
+        }
+      }
+      int rc = mlp_finalize(m); if (rc) return rc;
+      ++P.launches;
     } else if (op.kind == OP_ATTN) {
       resolve(P, op.a_in); resolve(P, op.a_out);
       op.a_bias = E.at<float>(op.w_name);
@@ -677,6 +720,7 @@ int run_ops(rs_plan& P, const std::vector<Op>& ops, const float* film_base, long
         rc = gn_launch(g, st);
         break;
       }
+      case OP_MLP: rc = mlp_launch(op.mlp, st); break;
       case OP_ATTN:
         rc = attn_launch(op.a_in, op.a_out, op.a_bias, P.e->cfg.swin_heads, P.e->cfg.swin_embed_dim, op.a_shift, st);
         break;
@@ -872,10 +916,13 @@ int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const fl
   for (size_t i = 0; i < prof.kind.size(); ++i) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]);
-    ms_by_kind[prof.kind[i]] += ms;
+    ms_by_kind[prof.kind[i] == (int)OP_MLP ? 0 : prof.kind[i]] += ms;
   }
   double fl = 0.0; int nc = 0;
-  for (const Op& op : p->ops) if (op.kind == OP_CONV) {
+  for (const Op& op : p->ops) if (op.kind == OP_MLP) {
+    fl += 4.0 * (double)op.mlp.in.N * op.mlp.in.H * op.mlp.in.W * op.mlp.E * (double)op.mlp.Hd;
+    ++nc;
+  } else if (op.kind == OP_CONV) {
     const ConvParams& c = op.conv.prm;
     const int cin_real = op.conv.in.tens == p->xin.tens ? p->e->cfg.in_channels + p->e->lq_feat_ch() : op.conv.in.C;
     fl += 2.0 * (double)c.Nimg * c.Hout * c.Wout * c.Cout * (double)c.num_taps * cin_real;
@@ -911,6 +958,8 @@ int rs_plan_profile_ops(rs_plan* p, const float* x, const float* timesteps, cons
                op.conv.stride, c.Hout, c.Wout, op.conv.in.C, c.Cout, op.conv.grid, c.BN, c.stages, op.w_name.c_str());
     } else if (op.kind == OP_GN) {
       snprintf(d, desc_stride, "gn %dx%d C=%d fused=%d %s", op.gn.in.H, op.gn.in.W, op.gn.in.C, (int)op.gn.fused, op.g_name.c_str());
+    } else if (op.kind == OP_MLP) {
+      snprintf(d, desc_stride, "mlp %dx%d E=%d Hd=%d grid=%d", op.mlp.in.H, op.mlp.in.W, op.mlp.E, op.mlp.Hd, op.mlp.grid);
     } else if (op.kind == OP_ATTN) {
       snprintf(d, desc_stride, "attn %dx%d shift=%d", op.a_in.H, op.a_in.W, op.a_shift);
     } else {

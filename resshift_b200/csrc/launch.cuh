@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "conv_gemm.cuh"
 #include "elementwise.cuh"
+#include "mlp_fused.cuh"
 #include "norm_act.cuh"
 #include "window_attn.cuh"
 
@@ -316,6 +317,7 @@ inline int conv_init() {   // once per process, outside any stream capture
     RS_CUDA_OK(cudaFuncSetAttribute(conv_gemm_sm100_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RS_CUDA_OK(cudaFuncSetAttribute(conv_gemm_sm100_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RS_CUDA_OK(cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    RS_CUDA_OK(cudaFuncSetAttribute(mlp_fused_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   return 0;
@@ -390,6 +392,71 @@ inline int gn_launch(const GnDesc& g, cudaStream_t st) {
   return 0;
 }
 
+// ---- fused Swin MLP ---------------------------------------------------------------------------
+struct MlpDesc {
+  View in, out, res;
+  bool has_res = true;
+  const __half* w1 = nullptr; const float* b1 = nullptr;    // fc1: [Hd][E] fp16
+  const __half* w2 = nullptr; const float* b2 = nullptr;    // fc2: [E][Hd] fp16
+  int E = 0, Hd = 0;
+  float* gn_part[2] = {nullptr, nullptr};
+  int gn_cstride[2] = {0, 0};
+  int gn_coff[2] = {0, 0};
+  long long* dbg = nullptr;
+  MlpParams prm;
+  int grid = 0; size_t smem = 0;
+};
+
+inline bool mlp_supported(int E, int Hd, int H, int W) {
+  bool fus = false;
+  conv_tile_slots(H, W, &fus);
+  return E % 64 == 0 && E <= 256 && Hd % kMlpHc == 0 && fus;
+}
+
+inline int mlp_finalize(MlpDesc& d) {
+  MlpParams& p = d.prm;
+  std::memset(&p, 0, sizeof(p));
+  const int H = d.in.H, W = d.in.W, N = d.in.N;
+  RS_CHECK(mlp_supported(d.E, d.Hd, H, W), "fused MLP: unsupported shape");
+  RS_CHECK(d.in.C == d.E && d.out.C == d.E, "fused MLP: channel mismatch");
+  p.E = d.E; p.Hd = d.Hd; p.bias1 = d.b1; p.bias2 = d.b2;
+  p.bw = pow2_floor_div(W, kConvBM);
+  p.bh = pow2_floor_div(H, kConvBM / p.bw);
+  p.bn = kConvBM / (p.bw * p.bh);
+  p.tiles_w = W / p.bw; p.tiles_h = H / p.bh;
+  const int tiles_n = (N + p.bn - 1) / p.bn;
+  p.Wout = W; p.Hout = H; p.Nimg = N;
+  p.ring = std::max(3, std::min(env_int("RS_MLP_RING", 4), 6));
+  p.slot_bytes = std::max(kConvBM * kConvBK * 2, d.E * kConvBK * 2);
+  p.has_res = d.has_res ? 1 : 0;
+  d.grid = p.tiles_w * p.tiles_h * tiles_n;
+  d.smem = (size_t)(d.E / 64) * 16384 + (size_t)p.ring * p.slot_bytes + 4 * 16384 + 1024 + 256;
+  RS_CHECK(d.smem <= 227 * 1024, "fused MLP: shared memory budget exceeded");
+  int rc = encode_act_map(&p.tmX, d.in.ptr, d.E, W, H, N, d.in.sW(), d.in.sH(), d.in.sN(), p.bw, p.bh, p.bn, 64);
+  if (rc) return rc;
+  rc = encode_weight_map(&p.tmW1, d.w1, d.E, d.Hd, kMlpHc); if (rc) return rc;
+  rc = encode_weight_map(&p.tmW2, d.w2, d.Hd, d.E, d.E); if (rc) return rc;
+  rc = encode_act_map(&p.tmOut, d.out.ptr, d.E, W, H, N, d.out.sW(), d.out.sH(), d.out.sN(), p.bw, p.bh, p.bn, 64);
+  if (rc) return rc;
+  if (d.has_res) {
+    rc = encode_act_map(&p.tmRes, d.res.ptr, d.E, W, H, N, d.res.sW(), d.res.sH(), d.res.sN(), p.bw, p.bh, p.bn, 64);
+    if (rc) return rc;
+  }
+  p.dbg = d.dbg;
+  p.gn_slots = p.tiles_w * p.tiles_h;
+  for (int i = 0; i < 2; ++i) { p.gn_part[i] = d.gn_part[i]; p.gn_cstride[i] = d.gn_cstride[i]; p.gn_coff[i] = d.gn_coff[i]; }
+  if (p.gn_part[0] == nullptr && p.gn_part[1] != nullptr) {
+    p.gn_part[0] = p.gn_part[1]; p.gn_cstride[0] = p.gn_cstride[1]; p.gn_coff[0] = p.gn_coff[1]; p.gn_part[1] = nullptr;
+  }
+  return 0;
+}
+
+inline int mlp_launch(const MlpDesc& d, cudaStream_t st) {
+  (void)launch_k(mlp_fused_sm100_kernel, dim3(d.grid), dim3(kMlpThreads), d.smem, st, d.prm);
+  RS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 inline size_t attn_smem_bytes(int E) {
   return (size_t)2 * 3 * 64 * kAttnPad * 2 + (size_t)64 * (E + 8) * 2 + 64 * sizeof(int);
 }
@@ -398,14 +465,18 @@ inline int attn_launch(const View& qkv, const View& out, const float* bias, int 
                        cudaStream_t st) {
   RS_CHECK(qkv.H % 8 == 0 && qkv.W % 8 == 0, "window attention needs H, W multiples of 8");
   RS_CHECK(E == heads * 32 && E % 8 == 0, "window attention kernel is specialised for head_dim 32");
-  WinAttnParams p{qkv.ptr, qkv.ld, out.ptr, out.ld, bias, qkv.N, qkv.H, qkv.W, heads, E, shift, 0.17677669529663687f};
   const int windows = qkv.N * (qkv.H / 8) * (qkv.W / 8);
+  // heads per CTA: all of them when there are plenty of windows, fewer (more CTAs) otherwise
+  int hpc = heads;
+  while (hpc > 1 && (long long)windows * (heads / hpc) < 4 * 148 && hpc % 2 == 0) hpc /= 2;
+  if (hpc > 1 && (long long)windows * (heads / hpc) < 4 * 148 && heads % hpc == 0) hpc = 1;
+  WinAttnParams p{qkv.ptr, qkv.ld, out.ptr, out.ld, bias, qkv.N, qkv.H, qkv.W, heads, E, shift, 0.17677669529663687f, hpc};
   if (env_is("RS_ATTN_IMPL", "simt")) {
     (void)launch_k(window_attn_simt_kernel, dim3(windows, heads), dim3(64), (size_t)0, st, p);
   } else {
     const size_t smem = attn_smem_bytes(E);
     RS_CHECK(smem <= 160 * 1024, "attention tile does not fit in shared memory");   // limit raised in conv_init()
-    (void)launch_k(window_attn_kernel, dim3(windows), dim3(128), smem, st, p);
+    (void)launch_k(window_attn_kernel, dim3(windows, heads / hpc), dim3(128), smem, st, p);
   }
   RS_CUDA_OK(cudaGetLastError());
   return 0;

@@ -30,6 +30,7 @@ struct WinAttnParams {
   int N, H, W, heads, E;
   int shift;                // 0 or 4
   float scale;              // head_dim^-0.5
+  int hpc;                  // heads per CTA (grid.y = heads / hpc): fewer heads per CTA when there are few windows
 };
 
 #ifdef __CUDACC__
@@ -72,7 +73,8 @@ __global__ void __launch_bounds__(128) window_attn_kernel(const WinAttnParams p)
   // [2 buffers][q | k | v][64][kAttnPad] halves, then the output tile [64][E + 8] halves, then the pixel table
   __half* sbuf = reinterpret_cast<__half*>(attn_smem);
   const int buf_halves = 3 * 64 * kAttnPad;
-  const int opitch = p.E + 8;
+  const int opitch = p.hpc * 32 + 8;
+  const int head0 = blockIdx.y * p.hpc;
   __half* sOut = sbuf + 2 * buf_halves;
   int* sPix = reinterpret_cast<int*>(sOut + 64 * opitch);
 
@@ -105,10 +107,11 @@ __global__ void __launch_bounds__(128) window_attn_kernel(const WinAttnParams p)
   const int row0 = warp * 16 + g;          // this lane's rows: row0 and row0 + 8
   const int la = p.shift ? swin_label(wy, row0 & 7, p.H, p.shift) : 0;     // (row0 + 8) & 7 == row0 & 7
 
-  stage_head(0, 0);
-  for (int head = 0; head < p.heads; ++head) {
-    const int buf = head & 1;
-    if (head + 1 < p.heads) { stage_head(head + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+  stage_head(head0, 0);
+  for (int hi = 0; hi < p.hpc; ++hi) {
+    const int head = head0 + hi;
+    const int buf = hi & 1;
+    if (hi + 1 < p.hpc) { stage_head(head + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
     const __half* sQ = sbuf + buf * buf_halves;
     const __half* sK = sQ + 64 * kAttnPad;
@@ -193,17 +196,17 @@ __global__ void __launch_bounds__(128) window_attn_kernel(const WinAttnParams p)
     const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
 #pragma unroll
     for (int dt = 0; dt < 4; ++dt) {
-      const int d = head * 32 + dt * 8 + 2 * t;
+      const int d = hi * 32 + dt * 8 + 2 * t;
       *reinterpret_cast<__half2*>(&sOut[row0 * opitch + d]) = __floats2half2_rn(o[dt][0] * inv0, o[dt][1] * inv0);
       *reinterpret_cast<__half2*>(&sOut[(row0 + 8) * opitch + d]) = __floats2half2_rn(o[dt][2] * inv1, o[dt][3] * inv1);
     }
     __syncthreads();      // everyone done with this head's buffer before it is refilled two iterations later
   }
-  // write the 64 x E tile as full rows
-  const int units = p.E >> 3;
+  // write this CTA's 64 x (hpc*32) slice as contiguous row segments
+  const int units = p.hpc * 4;
   for (int i = threadIdx.x; i < 64 * units; i += 128) {
     const int tok = i / units, u = i - tok * units;
-    *reinterpret_cast<uint4*>(p.out + (long long)sPix[tok] * p.out_ld + u * 8) =
+    *reinterpret_cast<uint4*>(p.out + (long long)sPix[tok] * p.out_ld + head0 * 32 + u * 8) =
         *reinterpret_cast<const uint4*>(&sOut[tok * opitch + u * 8]);
   }
 }

@@ -139,6 +139,35 @@ def test_conv2d_fused_groupnorm_statistics(case, msub):
     assert (q_got - q_ref).abs().max().item() <= 1e-4 * q_ref.abs().max().item()
 
 
+@pytest.mark.parametrize("case", [(2, 16, 16, 192, 768), (1, 64, 64, 64, 256), (3, 8, 8, 192, 768), (4, 32, 32, 192, 768)])
+def test_fused_mlp(case):
+    """out = residual + fc2(GELU(fc1(x))) in one kernel (hidden activations stay on chip, rounded to fp16 like the
+    unfused path rounds its stored intermediate)."""
+    N, H, W, E, Hd = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = G.nhwc16(torch.randn(N, E, H, W, device="cuda", generator=g))
+    res = G.nhwc16(torch.randn(N, E, H, W, device="cuda", generator=g))
+    w1 = torch.randn(Hd, E, device="cuda", generator=g) / E ** 0.5
+    b1 = torch.randn(Hd, device="cuda", generator=g) * 0.5
+    w2 = torch.randn(E, Hd, device="cuda", generator=g) / Hd ** 0.5
+    b2 = torch.randn(E, device="cuda", generator=g) * 0.5
+    w1p, _ = G.pack_weight(w1)
+    w2p, _ = G.pack_weight(w2)
+    outs = []
+    for _ in range(2):
+        out = torch.full((N, H, W, E), float("nan"), dtype=torch.float16, device="cuda")
+        _lib.check(G.L.rs_op_mlp(x.data_ptr(), N, H, W, E, Hd, w1p.data_ptr(), b1.data_ptr(), w2p.data_ptr(), b2.data_ptr(),
+                                 res.data_ptr(), out.data_ptr(), None, G.stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    xf = x.float().reshape(-1, E)
+    h = F.gelu(xf @ w1.half().float().T + b1).half().float()
+    ref = (h @ w2.half().float().T + b2 + res.float().reshape(-1, E)).reshape(N, H, W, E)
+    st = G.err_stats(outs[0], ref)
+    assert st["nan"] == 0 and st["max_abs"] <= _tol(ref), st
+
+
 @pytest.mark.parametrize("C,cfg", [(32, "plain"), (160, "silu"), (192, "plain"), (480, "film"), (1280, "film")])
 def test_groupnorm(C, cfg):
     g = torch.Generator(device="cuda").manual_seed(C)
