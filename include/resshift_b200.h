@@ -127,10 +127,14 @@ int rs_op_conv2d(const void* x, int N, int H, int W, int C, int ld, const void* 
 int rs_op_conv2d_stats(const void* x, int N, int H, int W, int C, int ld, const void* w_packed, int Ipad, const float* bias,
                        int Cout, int ksize, int stride, const void* residual, int res_ld, void* out, int out_ld, int act,
                        int bn, float* part, int cstride, int coff, int32_t* slots_out, void* stream);
+/* conv2d that may split its K loop over several CTAs (layers with few output tiles); scratch: 8*N*Ho*Wo*Cout floats */
+int rs_op_conv2d_splitk(const void* x, int N, int H, int W, int C, int ld, const void* w_packed, int Ipad, const float* bias,
+                        int Cout, int ksize, int stride, const void* residual, int res_ld, void* out, int out_ld, int act,
+                        float* part, int cstride, int coff, float* scratch, int32_t* splits_out, void* stream);
 /* profiling aid: `iters` launches of the same conv; per-CTA timeline of the last one in dbg (8 x u64 per CTA) */
 int rs_op_conv2d_timeline(const void* x, int N, int H, int W, int C, int ld, const void* w_packed, int Ipad, const float* bias,
                           int Cout, int ksize, int stride, void* out, int out_ld, int bn, int iters, void* dbg,
-                          int32_t* info, void* stream);
+                          int32_t* info, float* splitk_scratch_or_null, void* stream);
 /* GroupNorm32 (+ FiLM scale/shift, + SiLU) (reference models/basic_ops.py:15-17, models/unet.py:198-202) */
 int rs_op_groupnorm(const void* x, int N, int H, int W, int C, int ld, const float* gamma, const float* beta,
                     const float* film, long long film_sN, int silu, void* y, int y_ld, float* sums_scratch,

@@ -46,6 +46,9 @@ struct ConvParams {
   int tmem_cols;
   int cg;                // 1: one CTA per tile;  2: CTA pair (cluster of 2, tcgen05 cta_group::2): a 256-pixel x BN tile,
                          //    each CTA stages its own 128 pixels of A and HALF of the weight tile (halves the smem traffic of B)
+  int splitk;            // > 1: the K loop is cut into `splitk` ranges, one CTA (or pair) each; the epilogue then only
+                         //      stores fp32 partial accumulators to `partial` and splitk_reduce_kernel finishes the layer
+  float* partial;        // [splitk][Nimg*Hout*Wout pixels][Cout] fp32
   int msub;              // 128-pixel sub-tiles per CTA (1 or 2): two sub-tiles share every weight tile (fewer operand bytes per MMA)
   // epilogue
   const float* bias;                 // [Cout] fp32 or nullptr
@@ -101,10 +104,15 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
 
   // tile coordinates: CTA -> (channel tile, msub consecutive 128-pixel tiles)
   const uint32_t rank = kCG == 2 ? cluster_ctarank() : 0;    // leader = rank 0
-  const int unit = kCG == 2 ? (blockIdx.x >> 1) : blockIdx.x; // work unit: a CTA, or a CTA pair
+  int unit = kCG == 2 ? (blockIdx.x >> 1) : blockIdx.x;       // work unit: a CTA, or a CTA pair
+  const int split = unit % p.splitk;                          // which K range (fastest index: splits of a tile run together)
+  unit /= p.splitk;
   const int n_tile = unit % p.n_tiles;
   const int mt0 = kCG == 2 ? (unit / p.n_tiles) * 2 + (int)rank : (unit / p.n_tiles) * p.msub;
-  const int num_kb = p.num_taps * p.kchunks;
+  const int total_kb = p.num_taps * p.kchunks;
+  const int kb_begin = (int)((long long)total_kb * split / p.splitk);
+  const int kb_end = (int)((long long)total_kb * (split + 1) / p.splitk);
+  const int num_kb = kb_end - kb_begin;
   auto tile_origin = [&](int sub, int& tw_, int& th_, int& w0_, int& h0_, int& n0_) {
     int mt = mt0 + sub;
     tw_ = mt % p.tiles_w; mt /= p.tiles_w;
@@ -146,8 +154,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
       int tws[2], ths[2], w0s[2], h0s[2], n0s[2];
       for (int sub = 0; sub < p.msub; ++sub) tile_origin(sub, tws[sub], ths[sub], w0s[sub], h0s[sub], n0s[sub]);
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / p.kchunks;
-        const int kc = kb - tap * p.kchunks;
+        const int tap = (kb_begin + kb) / p.kchunks;
+        const int kc = (kb_begin + kb) - tap * p.kchunks;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
         uint8_t* sb = sa + p.msub * a_bytes;
@@ -219,7 +227,32 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
     tc_fence_after();
     if (dbg && threadIdx.x == 64) dbg[4] = global_timer_ns();
 
-    if (p.tma_out) {
+    if (p.splitk > 1) {
+      // ---------- split-K: raw fp32 partial sums, finished by splitk_reduce_kernel ----------
+      int tw, th, w0, h0, n0;
+      tile_origin(0, tw, th, w0, h0, n0);
+      const int w = w0 + lw, h = h0 + lh, n = n0 + ln;
+      const bool row_ok = (w < p.Wout) && (h < p.Hout) && (n < p.Nimg);
+      const long long pix = ((long long)n * p.Hout + h) * p.Wout + w;
+      const long long npix = (long long)p.Nimg * p.Hout * p.Wout;
+      float* prow = p.partial + ((long long)split * npix + pix) * p.Cout;
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int c = cpar * 16; c < p.BN; c += 32) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(trow + c, v);
+        tmem_ld_wait();
+        const int col = col0 + c;
+        if (!row_ok || col >= p.Cout) continue;
+        if (col + 16 <= p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(prow + col + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          for (int j = 0; j < 16 && col + j < p.Cout; ++j) prow[col + j] = __uint_as_float(v[j]);
+        }
+      }
+    } else if (p.tma_out) {
       // ---------- staged epilogue ----------
       // All operand stages are free now (every MMA that read them has retired), so the pipeline smem is reused.
       // Per sub-tile: BN/bc blocks of [128 rows x bc columns] fp16, swizzled like the TMA box — first the residual

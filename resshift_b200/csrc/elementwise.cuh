@@ -181,6 +181,100 @@ __global__ void prior_sample_kernel(const float* __restrict__ zy, const float* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// Split-K finish: out = act(sum_s partial[s] + bias) + residual, fp16 NHWC view (or fp32 NCHW), plus the
+// GroupNorm partial statistics of the result.  One CTA per (128-pixel slot, image) — the same slots the
+// conv epilogue would have produced; splits are summed in a fixed order, statistics reduced in a fixed tree.
+// ------------------------------------------------------------------------------------------------
+struct SplitKReduceParams {
+  const float* partial;     // [S][N*HW][C]
+  int S, N, HW, C;
+  const float* bias;
+  const __half* residual; long long res_sN; int res_ld;
+  __half* out; long long out_sN; int out_ld;
+  int act;
+  int rows_per_slot, slots;
+  int cols_per_cta;         // multiple of 8; grid.z = ceil(C / cols_per_cta)
+  float* gn_part[2]; int gn_cstride[2]; int gn_coff[2];
+};
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitKReduceParams p) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float s_red[];       // [lanes][cols_per_cta][2]
+  const int c_begin = blockIdx.z * p.cols_per_cta;
+  const int ccols = min(p.cols_per_cta, p.C - c_begin);
+  const int vecs = ccols >> 3;
+  const int lanes = blockDim.x / vecs;
+  const int n = blockIdx.y, slot = blockIdx.x;
+  const int vec = threadIdx.x % vecs, rl = threadIdx.x / vecs;
+  const long long npix = (long long)p.N * p.HW;
+  const bool want_stats = p.gn_part[0] != nullptr;
+  if (rl < lanes) {
+    float ssum[8], qsum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ssum[j] = 0.f; qsum[j] = 0.f; }
+    const int r0 = slot * p.rows_per_slot, r1 = min(r0 + p.rows_per_slot, p.HW);
+    const int c = c_begin + vec * 8;
+    float bs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bs[j] = p.bias ? p.bias[c + j] : 0.f;
+    for (int r = r0 + rl; r < r1; r += lanes) {
+      const long long pix = (long long)n * p.HW + r;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int s = 0; s < p.S; ++s) {
+        const float4* src = reinterpret_cast<const float4*>(p.partial + ((long long)s * npix + pix) * p.C + c);
+        const float4 a = src[0], b = src[1];
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = acc[j] + bs[j];
+        if (p.act == 1) v = gelu_erf_f(v); else if (p.act == 2) v = silu_f(v);
+        acc[j] = v;
+      }
+      if (p.residual) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(p.residual + n * p.res_sN + (long long)r * p.res_ld + c);
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+      }
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+      *reinterpret_cast<uint4*>(p.out + n * p.out_sN + (long long)r * p.out_ld + c) = o;
+      if (want_stats) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(oh[j]);
+          ssum[2 * j] += f.x; qsum[2 * j] += f.x * f.x;
+          ssum[2 * j + 1] += f.y; qsum[2 * j + 1] += f.y * f.y;
+        }
+      }
+    }
+    if (want_stats) {
+      float* dst = s_red + ((size_t)rl * ccols + vec * 8) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { dst[2 * j] = ssum[j]; dst[2 * j + 1] = qsum[j]; }
+    }
+  }
+  if (!want_stats) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * ccols; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += s_red[(size_t)l * ccols * 2 + i];
+    const int ch = c_begin + (i >> 1), m = i & 1;
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+      if (p.gn_part[d])
+        p.gn_part[d][(((size_t)n * p.slots + slot) * p.gn_cstride[d] + p.gn_coff[d] + ch) * 2 + m] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Weight repacking (load time): fp32 OIHW -> fp16 [O][kh][kw][Ipad]; fp32 [O, I] -> fp16 [O][Ipad]
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_conv_weight_kernel(const float* __restrict__ src, __half* __restrict__ dst, int O, int I,

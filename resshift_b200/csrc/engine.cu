@@ -276,6 +276,7 @@ struct Op {
   std::string w_name, b_name, g_name;   // parameter names resolved at bind
   size_t stats_off = 0;                 // GroupNorm: offset of its partial-sum buffer inside the stats region
   bool to_f32 = false;                  // conv: writes the fp32 NCHW model output
+  int split_tens = -1;                  // conv: workspace tensor holding split-K partial sums (or -1)
   struct StatDst { int list; int op; int coff; };
   std::vector<StatDst> stat_dst;        // conv: GroupNorm ops whose statistics this conv's epilogue produces
 };
@@ -345,6 +346,16 @@ struct Builder {
     if (res) { op.conv.res = *res; op.conv.has_res = true; }
     op.w_name = name + ".weight"; op.b_name = name + ".bias";
     op.to_f32 = out_f32;
+    if (out && !out_f32 && env_int("RS_CONV_SPLITK", 0) != 1) {       // split-K for layers with too few tiles
+      const TileConfig tc = conv_preview_config(in.N, in.H, in.W, in.C, cout, ksize, stride, true);
+      if (tc.splitk > 1) {
+        op.conv.allow_split = true;
+        const size_t bytes = (size_t)tc.splitk * in.N * (in.H / stride) * (in.W / stride) * cout * sizeof(float);
+        op.split_tens = P.new_tensor(bytes);
+        Tensor& tz = P.tensors[op.split_tens];
+        tz.first = tz.last = opi();
+      }
+    }
     const int i = opi();
     P.touch(in, i); if (out) P.touch(*out, i); if (res) P.touch(*res, i);
     cur->push_back(op);
@@ -652,11 +663,12 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       RS_CHECK(w != nullptr, "missing parameter " + op.w_name);
       d.wt = E.at<__half>(op.w_name); d.ipad = w->ipad; d.bias = E.at<float>(op.b_name);
       d.out_f32 = op.to_f32 ? P.out_f32 : nullptr;
+      d.partial = op.split_tens >= 0 ? reinterpret_cast<float*>(P.ws + P.tensors[op.split_tens].off) : nullptr;
       // the first conv reads the channel-padded packed input: expose the padded width to the kernel
       if (d.in.C < d.ipad && d.in.ld >= d.ipad && d.in.tens == P.xin.tens) d.in.C = d.ipad;
       if (d.in.C < d.ipad && P.fe_in.tens >= 0 && d.in.tens == P.fe_in.tens) d.in.C = d.ipad;
       int rc = conv_finalize(d); if (rc) return rc;
-      ++P.launches;
+      P.launches += d.prm.splitk > 1 ? 2 : 1;
     } else if (op.kind == OP_GN) {
       resolve(P, op.gn.in); resolve(P, op.gn.out);
       op.gn.gamma = E.at<float>(op.g_name + ".weight"); op.gn.beta = E.at<float>(op.g_name + ".bias");

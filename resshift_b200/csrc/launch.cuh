@@ -141,6 +141,10 @@ struct ConvDesc {
   int act = ACT_NONE;
   int bn_override = 0;
   unsigned long long* dbg = nullptr;
+  float* partial = nullptr;       // split-K scratch [S][pixels][Cout] fp32 (caller-provided when the plan chose S > 1)
+  bool allow_split = false;
+  SplitKReduceParams red;         // filled by finalize() when S > 1
+  int red_grid_x = 0, red_grid_z = 1; size_t red_smem = 0;
   // fused GroupNorm partial statistics of the output (up to two consumers)
   float* gn_part[2] = {nullptr, nullptr};
   int gn_cstride[2] = {0, 0};
@@ -151,14 +155,14 @@ struct ConvDesc {
   int grid = 0; size_t smem = 0;
 };
 
-struct TileConfig { int BN = 0, msub = 1, stages = 2, occ = 1, cg = 1; double est_cycles = 1e30; };
+struct TileConfig { int BN = 0, msub = 1, stages = 2, occ = 1, cg = 1, splitk = 1; double est_cycles = 1e30; };
 
 // Cost model calibrated on B200 timelines (profiles/r1_s5_*, r1_s6_*).  Per 64-channel k-block and 128-pixel tile the
 // tensor pipe needs 2*BN cycles; every operand byte crosses shared memory twice (TMA write + UMMA read, 128 B/clk
 // per SM), which is what actually bounds a single-CTA tile (A 16 KB + B BN*128 B);  a CTA pair (cg = 2,
 // tcgen05 cta_group::2) stages only half of B per SM.  Shallow rings are additionally latency-bound (~3000 cycles
 // per load).  The epilogue (~18 cycles per column + set-up) hides under a co-resident CTA; whole waves are counted.
-inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn) {
+inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn, bool allow_split = false) {
   const int f_msub = env_int("RS_CONV_MSUB", 0), f_occ = env_int("RS_CONV_OCC", 0), f_stages = env_int("RS_CONV_STAGES", 0);
   const int f_cg = env_int("RS_CONV_CG", 0);
   TileConfig best;
@@ -181,21 +185,49 @@ inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn
           const double smem_cycles = (sbytes + ms * (kConvBM * kConvBK * 2.0 + (cand / cg) * kConvBK * 2.0)) / 128.0;
           // SM time for every resident CTA to advance one k-block: tensor / smem work of each, or the load latency
           // amortised over the ring depth
-          const double kb_cycles = std::max(occ * std::max(ms * 2.0 * cand, smem_cycles), 3000.0 / st);
+          // load latency: ~3000 cycles when many tiles share each weight tile (L2 hits), ~7500 when the layer has so few
+          // pixel tiles that every weight tile is a fresh HBM read for a handful of CTAs (profiles/r1_s12_smallm_sweep.log)
+          const double load_lat = m_tiles >= 64 ? 3000.0 : 7500.0;
+          const double kb_cycles = std::max(occ * std::max(ms * 2.0 * cand, smem_cycles), load_lat / st);
           const double epi = 18.0 * cand * ms + 3000.0 + (cg == 2 ? 2500.0 : 0.0);  // + pipeline fill / set-up (+ cluster syncs)
           const long long units = (long long)((m_tiles + cg * ms - 1) / (cg * ms)) * n_tiles;   // CTAs or CTA pairs
           const double slots = (cg == 2 ? 74.0 : 148.0) * occ;
-          const double waves = std::ceil((double)units / slots);
-          const double round = num_kb * kb_cycles + (occ == 2 ? 0.5 * epi : epi);
-          const double total = waves * round;
-          if (total < best.est_cycles) {
-            best.est_cycles = total; best.BN = cand; best.msub = ms; best.stages = st; best.occ = occ; best.cg = cg;
+          // split-K: S CTAs (pairs) share one output tile's K loop; costs an fp32 round trip + a small reduce kernel
+          const int f_split = env_int("RS_CONV_SPLITK", 0);
+          const int kSplits[6] = {1, 2, 3, 4, 6, 8};
+          for (int si = 0; si < 6; ++si) {
+            const int S = kSplits[si];
+            if (S > 1 && (!allow_split || ms != 1 || num_kb / S < 6)) continue;
+            if (f_split && allow_split && ms == 1 && num_kb / f_split >= 6 && S != f_split) continue;
+            const double waves = std::ceil((double)units * S / slots);
+            const double kbs = std::ceil((double)num_kb / S);
+            const double round = kbs * kb_cycles + (occ == 2 ? 0.5 * epi : epi);
+            // fp32 partials: written once by the conv epilogue and read once by the reduce kernel (~2 KB/clk chip-wide
+            // each way in practice), plus a second kernel launch / drain (~10 us of fixed cost for the pair)
+            const double part_bytes = 4.0 * m_tiles * 128.0 * cout16 * S;
+            const double total = waves * round + (S > 1 ? 19000.0 + 2.0 * part_bytes / 2048.0 : 0.0);
+            if (total < best.est_cycles) {
+              best.est_cycles = total; best.BN = cand; best.msub = ms; best.stages = std::min(st, (int)std::max(2.0, kbs));
+              best.occ = occ; best.cg = cg; best.splitk = S;
+            }
           }
         }
       }
     }
   }
   return best;
+}
+
+// geometry-only preview of the configuration conv_finalize() will choose (used at plan time to size split-K scratch)
+inline TileConfig conv_preview_config(int N, int Hin, int Win, int Cin, int Cout, int ksize, int stride, bool allow_split) {
+  const int Hout = Hin / stride, Wout = Win / stride;
+  const int bw = pow2_floor_div(Wout, kConvBM);
+  const int bh = pow2_floor_div(Hout, kConvBM / bw);
+  const int bn = kConvBM / (bw * bh);
+  const int m_tiles = (Wout / bw) * (Hout / bh) * ((N + bn - 1) / bn);
+  const bool contiguous = (bw == Wout) || (bh == 1);
+  const int num_kb = ksize * ksize * ((Cin + kConvBK - 1) / kConvBK);
+  return pick_tile_config(m_tiles, (Cout + 15) / 16 * 16, num_kb, env_int("RS_CONV_BN", 0), allow_split && contiguous && bn <= 2);
 }
 
 inline int conv_finalize(ConvDesc& d) {
@@ -223,9 +255,12 @@ inline int conv_finalize(ConvDesc& d) {
   // column per sub-tile) hides under the other resident CTA when two fit; whole waves of CTAs are counted.
   const int cout16 = (d.Cout + 15) / 16 * 16;
   const int num_kb = p.num_taps * p.kchunks;
-  const TileConfig tc = pick_tile_config(m_tiles, cout16, num_kb, d.bn_override ? d.bn_override : env_int("RS_CONV_BN", 0));
+  const bool contiguous_tiles = (p.bw == Wout) || (p.bh == 1);
+  const bool can_split = d.allow_split && d.partial != nullptr && contiguous_tiles && p.bn <= 2 && d.has_out && !d.out_f32;
+  const TileConfig tc = pick_tile_config(m_tiles, cout16, num_kb, d.bn_override ? d.bn_override : env_int("RS_CONV_BN", 0), can_split);
   const int BN = tc.BN, msub = tc.msub, stages = tc.stages, cg = tc.cg;
   p.cg = cg;
+  p.splitk = tc.splitk; p.partial = d.partial;
   RS_CHECK(BN >= 16 && BN <= 256 && BN % 16 == 0, "no valid tile configuration");
   p.BN = BN; p.n_tiles = (cout16 + BN - 1) / BN;
   p.msub = msub;
@@ -235,7 +270,7 @@ inline int conv_finalize(ConvDesc& d) {
   p.stages = stages;
   d.smem = (size_t)stages * stage_bytes + 1024 + 256;
   RS_CHECK(d.smem <= 227 * 1024, "shared memory budget exceeded");
-  d.grid = cg == 2 ? ((m_tiles + 1) / 2) * p.n_tiles * 2 : (m_tiles / msub) * p.n_tiles;
+  d.grid = (cg == 2 ? ((m_tiles + 1) / 2) * p.n_tiles * 2 : (m_tiles / msub) * p.n_tiles) * p.splitk;
   // taps
   if (d.stride == 1) {
     int t = 0;
@@ -265,7 +300,7 @@ inline int conv_finalize(ConvDesc& d) {
   p.out_f32_nchw = d.out_f32;
   p.dbg = d.dbg;
   // staged epilogue (TMA store / TMA residual load) for fp16 NHWC outputs
-  p.tma_out = (d.has_out && !d.out_f32 && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt")) ? 1 : 0;
+  p.tma_out = (d.has_out && !d.out_f32 && p.splitk == 1 && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt")) ? 1 : 0;
   p.tma_res = (p.tma_out && d.has_res) ? 1 : 0;
   p.epi_bc = (BN % 64 == 0) ? 64 : (BN % 32 == 0 ? 32 : 16);
   if (p.tma_out) {
@@ -287,6 +322,31 @@ inline int conv_finalize(ConvDesc& d) {
   }
   if (p.gn_part[0] == nullptr && p.gn_part[1] != nullptr) {
     p.gn_part[0] = p.gn_part[1]; p.gn_cstride[0] = p.gn_cstride[1]; p.gn_coff[0] = p.gn_coff[1]; p.gn_part[1] = nullptr;
+  }
+  if (p.splitk > 1) {
+    // the conv kernel only produces fp32 partial sums; bias / activation / residual / fp16 store / GroupNorm partials
+    // happen in the reduce kernel, one CTA per (128-pixel slot, image)
+    SplitKReduceParams& r = d.red;
+    std::memset(&r, 0, sizeof(r));
+    r.partial = d.partial; r.S = p.splitk; r.N = N; r.HW = Hout * Wout; r.C = d.Cout;
+    r.bias = d.bias; r.act = d.act;
+    if (d.has_res) { r.residual = d.res.ptr; r.res_sN = d.res.sN(); r.res_ld = d.res.ld; }
+    r.out = d.out.ptr; r.out_sN = d.out.sN(); r.out_ld = d.out.ld;
+    r.rows_per_slot = p.bw * p.bh; r.slots = p.tiles_w * p.tiles_h;
+    for (int i = 0; i < 2; ++i) { r.gn_part[i] = d.gn_part[i]; r.gn_cstride[i] = d.gn_cstride[i]; r.gn_coff[i] = d.gn_coff[i]; }
+    if (r.gn_part[0] == nullptr && r.gn_part[1] != nullptr) {
+      r.gn_part[0] = r.gn_part[1]; r.gn_cstride[0] = r.gn_cstride[1]; r.gn_coff[0] = r.gn_coff[1]; r.gn_part[1] = nullptr;
+    }
+    RS_CHECK(d.Cout % 8 == 0 && d.Cout <= 2048, "split-K reduce needs Cout % 8 == 0");
+    p.bias = nullptr; p.residual = nullptr; p.act = ACT_NONE; p.gn_part[0] = p.gn_part[1] = nullptr;
+    d.red_grid_x = r.slots;
+    // column blocks so that the reduce kernel fills the machine even with one slot per image
+    int cpc = d.Cout;
+    while (cpc > 64 && cpc % 16 == 0 && (long long)r.slots * N * (d.Cout / cpc) < 2 * 148) cpc /= 2;
+    r.cols_per_cta = cpc;
+    d.red_grid_z = (d.Cout + cpc - 1) / cpc;
+    const int lanes = 256 / std::max(1, cpc / 8);
+    d.red_smem = (size_t)std::max(1, lanes) * cpc * 2 * sizeof(float);
   }
   // tensor maps + SIMT mirrors
   ConvSimtSrc& s = d.simt;
@@ -333,6 +393,8 @@ inline int conv_launch(const ConvDesc& d, cudaStream_t st) {
       (void)launch_kc(conv_gemm_sm100_kernel<2>, dim3(d.grid), dim3(kConvThreads), (size_t)(d.smem), st, 2, d.prm);
     else
       (void)launch_kc(conv_gemm_sm100_kernel<1>, dim3(d.grid), dim3(kConvThreads), (size_t)(d.smem), st, 1, d.prm);
+    if (d.prm.splitk > 1)
+      (void)launch_k(splitk_reduce_kernel, dim3(d.red_grid_x, d.prm.Nimg, d.red_grid_z), dim3(256), d.red_smem, st, d.red);
   }
   RS_CUDA_OK(cudaGetLastError());
   return 0;

@@ -1,12 +1,11 @@
 #!/bin/bash
+# GPU session 13: calibrated split-K; full suite + bench
 mkdir -p gpurun_out
-timeout 200 python scripts/mlp_timeline.py > gpurun_out/mlp_tl.log 2>&1
-timeout 300 python -m pytest tests/test_gpu_ops.py -q -p no:cacheprovider -k "mlp or epilogue" > gpurun_out/tests_new.log 2>&1
-timeout 900 python -m pytest tests/test_gpu_unet.py -q -p no:cacheprovider > gpurun_out/tests_unet.log 2>&1
+timeout 1200 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/tests_all.log 2>&1
 timeout 300 python scripts/profile_ops.py 16 > gpurun_out/ops_b16.log 2>&1
-timeout 400 python bench.py --steps 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1
-cat gpurun_out/mlp_tl.log
-tail -4 gpurun_out/tests_new.log
-tail -4 gpurun_out/tests_unet.log
-head -24 gpurun_out/ops_b16.log
-tail -c 500 gpurun_out/bench.log
+timeout 500 python bench.py > gpurun_out/bench.log 2>&1
+timeout 300 python bench.py --batch 1 --steps 5 --no-cpu-baseline > gpurun_out/bench_b1.log 2>&1
+tail -5 gpurun_out/tests_all.log
+head -20 gpurun_out/ops_b16.log
+grep -o '"ms_per_denoise_step": [0-9.]*' gpurun_out/bench.log gpurun_out/bench_b1.log
+grep -o '"value": [0-9.]*' gpurun_out/bench.log | head -3

@@ -139,6 +139,46 @@ def test_conv2d_fused_groupnorm_statistics(case, msub):
     assert (q_got - q_ref).abs().max().item() <= 1e-4 * q_ref.abs().max().item()
 
 
+@pytest.mark.parametrize("force", [0, 2, 4])
+@pytest.mark.parametrize("case", [(16, 8, 8, 640, 640, 3), (3, 16, 16, 320, 320, 3), (5, 8, 8, 192, 192, 1), (2, 16, 16, 960, 320, 3)])
+def test_conv2d_split_k(case, force):
+    """Layers with few output tiles split their K loop over several CTAs; fp32 partial sums are combined in a fixed
+    order by the reduce kernel, which also applies bias / residual and emits the GroupNorm partial statistics."""
+    import ctypes as C
+    N, H, W, Ci, Co, k = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = G.nhwc16(torch.randn(N, Ci, H, W, device="cuda", generator=g))
+    w = torch.randn(Co, Ci, k, k, device="cuda", generator=g) / (Ci * k * k) ** 0.5
+    b = torch.randn(Co, device="cuda", generator=g)
+    res = G.nhwc16(torch.randn(N, Co, H, W, device="cuda", generator=g))
+    wp, ipad = G.pack_weight(w)
+    scratch = torch.empty(8 * N * H * W * Co, dtype=torch.float32, device="cuda")
+    if force:
+        os.environ["RS_CONV_SPLITK"] = str(force)
+    try:
+        outs, parts, used = [], [], []
+        for rep in range(2):
+            out = torch.full((N, H, W, Co), float("nan"), dtype=torch.float16, device="cuda")
+            part = torch.full((N * 64 * Co * 2,), float("nan"), dtype=torch.float32, device="cuda")
+            S = C.c_int32()
+            _lib.check(G.L.rs_op_conv2d_splitk(x.data_ptr(), N, H, W, Ci, Ci, wp.data_ptr(), ipad, b.data_ptr(), Co, k, 1,
+                                               res.data_ptr(), Co, out.data_ptr(), Co, 0, part.data_ptr(), Co, 0,
+                                               scratch.data_ptr(), C.byref(S), G.stream()))
+            torch.cuda.synchronize()
+            outs.append(out); parts.append(part.clone()); used.append(S.value)
+    finally:
+        os.environ.pop("RS_CONV_SPLITK", None)
+    print(f"[split-k] case {case} forced {force}: S = {used[0]}")
+    assert torch.equal(outs[0], outs[1]) and torch.equal(parts[0][~torch.isnan(parts[0])], parts[1][~torch.isnan(parts[1])])
+    ref = G.ref_conv(x, w, b, residual=res)
+    st = G.err_stats(G.nchw32(outs[0]), ref)
+    assert st["nan"] == 0 and st["max_abs"] <= _tol(ref), st
+    slots = max(1, H * W // 128)
+    pv = parts[0][:N * slots * Co * 2].view(N, slots, Co, 2)
+    of = outs[0].float()
+    assert (pv[..., 0].sum(1) - of.sum(dim=(1, 2))).abs().max().item() <= 1e-3 * (1 + of.sum(dim=(1, 2)).abs().max().item())
+
+
 @pytest.mark.parametrize("case", [(2, 16, 16, 192, 768), (1, 64, 64, 64, 256), (3, 8, 8, 192, 768), (4, 32, 32, 192, 768)])
 def test_fused_mlp(case):
     """out = residual + fc2(GELU(fc1(x))) in one kernel (hidden activations stay on chip, rounded to fp16 like the

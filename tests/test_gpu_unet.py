@@ -146,22 +146,31 @@ def test_loop_realsr_15_vs_reference_golden(golden_dir):
 
 
 def test_batch_independence_at_bench_size():
-    """BASELINE config 2 size (batch 16, full width): image i of the batched run == the same image run alone.
-    (Tiles of different images share CTAs at the 8x8 level; GroupNorm statistics are per image.)"""
+    """BASELINE config 2 size (batch 16, full width).  Tiles of different images share CTAs at the 8x8 level and
+    GroupNorm statistics are per image, so image i must not depend on its batch neighbours: bit-exact when only the
+    OTHER images change (every reduction has a fixed order, no atomics).  Against a batch-1 run the result agrees to
+    rounding noise only, because the planner picks other tile shapes / split-K factors for other batch sizes."""
     ucfg, _, m = _model("realsr")
     g = torch.Generator(device="cuda").manual_seed(7)
     x = torch.randn(16, 3, 64, 64, device="cuda", generator=g)
     lq = torch.rand(16, 3, 64, 64, device="cuda", generator=g) * 2 - 1
     t = torch.full((16,), 9, device="cuda")
-    full = m(x, t, lq=lq)
+    full = m(x, t, lq=lq).clone()
     assert not torch.isnan(full).any()
-    for i in (0, 5, 15):
+    again = m(x, t, lq=lq)
+    assert torch.equal(full, again)                                   # run-to-run bit reproducible
+    keep = [0, 5, 15]
+    x2, lq2 = torch.randn_like(x), torch.rand_like(lq) * 2 - 1
+    for i in keep:
+        x2[i], lq2[i] = x[i], lq[i]
+    other = m(x2, t, lq=lq2)
+    for i in keep:
+        assert torch.equal(other[i], full[i]), f"image {i} depends on its batch neighbours"
+    for i in (5,):
         one = m(x[i:i + 1], t[i:i + 1], lq=lq[i:i + 1])
         d = (one - full[i:i + 1]).abs()
-        print(f"[property] batch-16 vs single image {i}: max|d|={d.max().item():.3e} mean|d|={d.mean().item():.3e}")
-        # every reduction has a fixed order (no atomics) and per-image statistics never mix images, so a batched
-        # run must reproduce the single-image run bit for bit
-        assert d.max().item() == 0.0
+        print(f"[property] batch-16 vs batch-1 run of image {i}: max|d|={d.max().item():.3e} mean|d|={d.mean().item():.3e}")
+        assert d.max().item() <= 1e-2 and d.mean().item() <= 1e-3
     # and the batched result itself is right: image 5 against the CPU oracle
     from oracle import unet_oracle as uo
     sd = random_state_dict(ucfg, 0)
