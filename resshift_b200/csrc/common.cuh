@@ -63,7 +63,9 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// x * sigmoid(x): ex2 + approximate reciprocal (2 ulp), no IEEE-division fix-up sequence (the GroupNorm pass that
+// applies it is bound by instruction issue / MUFU, not by memory)
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 // exact-erf GELU (nn.GELU default, reference models/swin_transformer.py:18):  0.5 x (1 + erf(x / sqrt 2)).
 // erf(z) = sign(z) (1 - 2^P(|z|)) with P a degree-7 minimax-style fit of log2(erfc) on [0, 4] (clamped beyond):
 // |erf error| <= 4.3e-6, |GELU error| <= 6.4e-7 over all x — three orders below the fp16 rounding of the stored
@@ -79,8 +81,29 @@ __device__ __forceinline__ float gelu_erf_f(float v) {
   pz = fmaf(z, pz, 6.178960575e-06f);
   float ex;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(pz));
-  const float e = 1.0f - ex;                     // erf(|x| / sqrt 2)
-  return 0.5f * v * (1.0f + copysignf(e, v));
+  // 0.5 v (1 + sign(v) (1 - ex))  =  h + |h| - |h| ex   with h = v / 2
+  const float h = 0.5f * v;
+  return h + fmaf(-fabsf(h), ex, fabsf(h));
+}
+
+// Two GELUs at once on the packed fp32 pipe (fma.rn.f32x2, sm_100): same polynomial, half the FMA-pipe issue slots.
+__device__ __forceinline__ float2 gelu_erf_f2(float2 v) {
+  float2 z = __fmul2_rn(make_float2(fabsf(v.x), fabsf(v.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
+  z.x = fminf(z.x, 4.0f); z.y = fminf(z.y, 4.0f);
+  float2 pz = __ffma2_rn(z, make_float2(-2.177763781e-05f, -2.177763781e-05f), make_float2(5.068330793e-04f, 5.068330793e-04f));
+  pz = __ffma2_rn(z, pz, make_float2(-5.339398049e-03f, -5.339398049e-03f));
+  pz = __ffma2_rn(z, pz, make_float2(3.423144668e-02f, 3.423144668e-02f));
+  pz = __ffma2_rn(z, pz, make_float2(-1.528908461e-01f, -1.528908461e-01f));
+  pz = __ffma2_rn(z, pz, make_float2(-9.167589545e-01f, -9.167589545e-01f));
+  pz = __ffma2_rn(z, pz, make_float2(-1.628154397e+00f, -1.628154397e+00f));
+  pz = __ffma2_rn(z, pz, make_float2(6.178960575e-06f, 6.178960575e-06f));
+  float2 ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(pz.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(pz.y));
+  // 1 + sign(v) (1 - ex)  =  1 + s - s ex   with s = +-1
+  const float2 s = make_float2(copysignf(1.0f, v.x), copysignf(1.0f, v.y));
+  const float2 t = __ffma2_rn(make_float2(-s.x, -s.y), ex, make_float2(1.0f + s.x, 1.0f + s.y));
+  return __fmul2_rn(__fmul2_rn(v, make_float2(0.5f, 0.5f)), t);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -112,6 +135,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// cluster-scope flavours: arrive on a barrier that lives in another CTA of the cluster (address from mapa_u32) with
+// release semantics for this thread's earlier shared-memory writes, and the matching acquire on the waiting side
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded spin: a pipeline bug must not hang the GPU box (that is a strike); after ~2 s of
 // polling the kernel traps instead, which surfaces as a launch failure on the host.
 __device__ __forceinline__ uint64_t global_timer_ns() {
@@ -126,6 +167,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0xFFu) == 0 && global_timer_ns() - t0 > 2000000000ull) {
       printf("rs: mbarrier wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0xFFu) == 0 && global_timer_ns() - t0 > 2000000000ull) {
+      printf("rs: mbarrier (cluster) wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
       __trap();
     }
   }
@@ -168,6 +221,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// TMA tile load multicast to every CTA of `cta_mask` (same shared-memory offset and same mbarrier offset in each)
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -192,6 +253,9 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// the staged shared memory has been READ by every committed store (it may be reused / the CTA may exit); the global
+// writes themselves complete asynchronously, at the latest at kernel completion
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (TMA store reads them)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -253,6 +317,14 @@ __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t cta_mask
                : "memory");
 }
 
+// single-CTA MMAs, arrival delivered to the same barrier offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -282,6 +354,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// same, with the destination registers of the load as in/out operands: every use of v is ordered after the wait
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
 //   rows are 128 B (64 fp16) apart, 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100).

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint64_t* res_bar = tmem_full_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + 256);   // [BN] bias of this channel tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -223,6 +224,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
     const int col0 = n_tile * p.BN;
     const int etid = threadIdx.x - 64;               // 0..255 among epilogue threads
 
+    // the channel tile's bias goes to shared memory while the main loop runs (broadcast reads in the epilogue)
+    for (int i = etid; i < p.BN; i += 32 * kConvEpiWarps)
+      s_bias[i] = (p.bias && col0 + i < p.Cout) ? __ldg(p.bias + col0 + i) : 0.f;
+    named_bar_sync(1, 32 * kConvEpiWarps);
+
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (dbg && threadIdx.x == 64) dbg[4] = global_timer_ns();
@@ -286,17 +292,22 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + sub * p.BN;
         uint8_t* sblk = smem + (size_t)sub * sub_bytes;
         float* wsum = wsum_all + (size_t)sub * 4 * p.BN * 2;                           // [4 quads][BN][2]
+        uint32_t vn[16];
+        if (cpar * 16 < p.BN) tmem_ld16(trow + cpar * 16, vn);
         for (int c = cpar * 16; c < p.BN; c += 32) {
-          uint32_t v[16];
-          tmem_ld16(trow + c, v);
-          tmem_ld_wait();
+          tmem_ld_wait16(vn);
           const int col = col0 + c;
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(vn[j]);
+          if (c + 32 < p.BN) tmem_ld16(trow + c + 32, vn);     // next chunk's TMEM read overlaps this chunk's arithmetic
+          {
+            const float4* bp = reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += (col + j < p.Cout) ? __ldg(p.bias + col + j) : 0.f;
+            for (int j = 0; j < 4; ++j) {
+              const float4 b4 = bp[j];
+              f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+            }
           }
           if (p.act == ACT_GELU) {
 #pragma unroll
@@ -371,6 +382,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
       }
       fence_proxy_async_smem();
       named_bar_sync(1, 32 * kConvEpiWarps);
+      if (dbg && etid == 0) dbg[6] = global_timer_ns();
       if (etid == 0) {
         for (int sub = 0; sub < p.msub; ++sub) {
           int tw, th, w0, h0, n0;
@@ -415,7 +427,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
           }
         }
       }
-      if (etid == 0) tma_store_wait_all();
+      if (etid == 0) tma_store_wait_read();
     } else {
       // ---------- direct epilogue (fp32 NCHW model head, or RS_CONV_EPI=direct) ----------
       for (int sub = 0; sub < p.msub; ++sub) {

@@ -181,7 +181,7 @@ inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn
           const int budget = (occ == 2 ? 111 : 222) * 1024 - 2048;
           int st = std::min(std::min(8, std::max(2, num_kb)), budget / sbytes);
           if (f_stages) st = f_stages;
-          if (st < 2 || (size_t)st * sbytes + 1280 > (size_t)(occ == 2 ? 113 : 227) * 1024) continue;
+          if (st < 2 || (size_t)st * sbytes + 2304 > (size_t)(occ == 2 ? 113 : 227) * 1024) continue;
           const double smem_cycles = (sbytes + ms * (kConvBM * kConvBK * 2.0 + (cand / cg) * kConvBK * 2.0)) / 128.0;
           // SM time for every resident CTA to advance one k-block: tensor / smem work of each, or the load latency
           // amortised over the ring depth
@@ -268,7 +268,7 @@ inline int conv_finalize(ConvDesc& d) {
   p.tmem_cols = cols;
   const int stage_bytes = msub * kConvBM * kConvBK * 2 + (BN / cg) * kConvBK * 2;
   p.stages = stages;
-  d.smem = (size_t)stages * stage_bytes + 1024 + 256;
+  d.smem = (size_t)stages * stage_bytes + 1024 + 256 + 1024;   // ring + alignment slack + barriers + bias tile
   RS_CHECK(d.smem <= 227 * 1024, "shared memory budget exceeded");
   d.grid = (cg == 2 ? ((m_tiles + 1) / 2) * p.n_tiles * 2 : (m_tiles / msub) * p.n_tiles) * p.splitk;
   // taps
@@ -442,14 +442,14 @@ inline int gn_launch(const GnDesc& g, cudaStream_t st) {
     (void)launch_k(gn_stats_kernel, dim3(chunks, N), dim3(256), (size_t)lanes * C * 2 * sizeof(float), st, sp);
     RS_CUDA_OK(cudaGetLastError());
   }
-  // apply: ~2 CTAs per SM in total (each CTA re-derives the per-channel affine from the partials, so fewer, fatter
-  // CTAs keep that prologue traffic small), at least 32 rows each
-  int actas = std::max(1, std::min((HW + 31) / 32, (148 * 2 + N - 1) / N));
+  // apply: ~4 CTAs per SM in total, all resident at once (each CTA re-derives the per-channel affine from the
+  // partials — a latency, not a bandwidth cost), at least 16 rows each
+  int actas = std::max(1, std::min((HW + 15) / 16, (148 * 4 + N - 1) / N));
   const int arows = (HW + actas - 1) / actas;
   actas = (HW + arows - 1) / arows;
   GnApplyParams ap{g.in.ptr, g.in.sN(), g.in.ld, g.out.ptr, g.out.sN(), g.out.ld, C, HW, N, g.part, slots,
                    g.gamma, g.beta, g.film, g.film_sN, g.silu, arows, 1e-5f};
-  (void)launch_k(gn_apply_kernel, dim3(actas, N), dim3(256), (size_t)(2 * C + 64) * sizeof(float), st, ap);
+  (void)launch_k(gn_apply_kernel, dim3(actas, N), dim3(256), (size_t)(4 * C + 64) * sizeof(float), st, ap);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -488,16 +488,32 @@ inline int mlp_finalize(MlpDesc& d) {
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh;
   const int tiles_n = (N + p.bn - 1) / p.bn;
   p.Wout = W; p.Hout = H; p.Nimg = N;
-  p.ring = std::max(3, std::min(env_int("RS_MLP_RING", 4), 6));
-  p.slot_bytes = std::max(kConvBM * kConvBK * 2, d.E * kConvBK * 2);
+  // shared memory: X (E/64 tiles) + two H buffers + barriers + both bias vectors, the rest is weight ring slots:
+  // one hidden chunk of each stream (E/64 fc1 tiles, kMlpHc/64 fc2 tiles), spare slots to the fc1 ring first
+  const size_t kW1 = (size_t)kMlpHc * 128;
+  const size_t slot2 = (size_t)d.E * 128;
+  const int kHT = kMlpHc / 64, kx = d.E / 64;
+  const size_t fixed = (size_t)kx * 16384 + (size_t)2 * kHT * 16384 + 1024 + 512 + (size_t)(d.Hd + d.E) * sizeof(float);
+  RS_CHECK(fixed + kHT * slot2 + (size_t)kx * kW1 <= 227 * 1024, "fused MLP: not enough shared memory for the weight rings");
+  const size_t budget = 227 * 1024 - fixed;
+  p.ring2 = kHT;
+  p.ring1 = (int)std::min<size_t>(12, (budget - (size_t)p.ring2 * slot2) / kW1);
+  {
+    const size_t spare = budget - (size_t)p.ring2 * slot2 - (size_t)p.ring1 * kW1;
+    p.ring2 += (int)std::min<size_t>(2, spare / slot2);
+  }
   p.has_res = d.has_res ? 1 : 0;
   d.grid = p.tiles_w * p.tiles_h * tiles_n;
-  d.smem = (size_t)(d.E / 64) * 16384 + (size_t)p.ring * p.slot_bytes + 4 * 16384 + 1024 + 256;
+  {
+    const int want = env_int("RS_MLP_CLUSTER", 4);
+    p.cluster = (want >= 4 && d.grid % 4 == 0 && kMlpHc % 32 == 0 && d.E % 32 == 0) ? 4 : ((want >= 2 && d.grid % 2 == 0) ? 2 : 1);
+  }
+  d.smem = fixed + (size_t)p.ring1 * kW1 + (size_t)p.ring2 * slot2;
   RS_CHECK(d.smem <= 227 * 1024, "fused MLP: shared memory budget exceeded");
   int rc = encode_act_map(&p.tmX, d.in.ptr, d.E, W, H, N, d.in.sW(), d.in.sH(), d.in.sN(), p.bw, p.bh, p.bn, 64);
   if (rc) return rc;
-  rc = encode_weight_map(&p.tmW1, d.w1, d.E, d.Hd, kMlpHc); if (rc) return rc;
-  rc = encode_weight_map(&p.tmW2, d.w2, d.Hd, d.E, d.E); if (rc) return rc;
+  rc = encode_weight_map(&p.tmW1, d.w1, d.E, d.Hd, kMlpHc / p.cluster); if (rc) return rc;   // each CTA fetches 1/cluster of a tile
+  rc = encode_weight_map(&p.tmW2, d.w2, d.Hd, d.E, d.E / p.cluster); if (rc) return rc;
   rc = encode_act_map(&p.tmOut, d.out.ptr, d.E, W, H, N, d.out.sW(), d.out.sH(), d.out.sN(), p.bw, p.bh, p.bn, 64);
   if (rc) return rc;
   if (d.has_res) {
@@ -514,7 +530,7 @@ inline int mlp_finalize(MlpDesc& d) {
 }
 
 inline int mlp_launch(const MlpDesc& d, cudaStream_t st) {
-  (void)launch_k(mlp_fused_sm100_kernel, dim3(d.grid), dim3(kMlpThreads), d.smem, st, d.prm);
+  (void)launch_kc(mlp_fused_sm100_kernel, dim3(d.grid), dim3(kMlpThreads), d.smem, st, d.prm.cluster, d.prm);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }

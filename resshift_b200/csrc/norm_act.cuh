@@ -99,21 +99,33 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const GnStatsParams p) {
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p) {
   pdl_trigger();
-  pdl_wait();
-  extern __shared__ float s_ab[];    // a[C], b[C], mean[32], rstd[32]
+  extern __shared__ float s_ab[];    // a[C], b[C], gamma[C], beta[C], mean[32], rstd[32]
   float* s_a = s_ab;
   float* s_b = s_ab + p.C;
-  float* s_mean = s_ab + 2 * p.C;
+  float* s_g = s_ab + 2 * p.C;
+  float* s_be = s_ab + 3 * p.C;
+  float* s_mean = s_ab + 4 * p.C;
   float* s_rstd = s_mean + 32;
   const int n = blockIdx.y;
   const int cpg = p.C / 32;
-  // per-channel totals over the slots (independent loads, fixed order), staged in s_a / s_b; then per-group
-  // mean / rstd in a fixed order over the group's channels
+  // layer parameters do not depend on the producing kernel: fetch them while it drains
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) { s_g[c] = __ldg(p.gamma + c); s_be[c] = __ldg(p.beta + c); }
+  pdl_wait();
+  // per-channel totals over the slots (independent loads, fixed order), staged in s_a / s_b together with the FiLM
+  // pair (kept in registers: a thread owns the same channels in both passes); then per-group mean / rstd in a fixed
+  // order over the group's channels
+  float f_sc[8], f_sh[8];            // C <= 2048 -> at most 8 channels per thread
   {
     const float* part = p.part + (size_t)n * p.slots * p.C * 2;
-    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const float* f = p.film ? p.film + n * p.film_sN : nullptr;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int c = threadIdx.x + it * 256;
+      if (c >= p.C) break;
+      f_sc[it] = f ? 1.0f + f[c] : 1.0f;
+      f_sh[it] = f ? f[p.C + c] : 0.0f;
       float s = 0.f, q = 0.f;
       int sl = 0;
       for (; sl + 4 <= p.slots; sl += 4) {
@@ -141,17 +153,18 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const int g = c / cpg;
-    float a = s_rstd[g] * p.gamma[c];
-    float b = p.beta[c] - s_mean[g] * a;
-    if (p.film) {
-      const float* f = p.film + n * p.film_sN;
-      const float sc = 1.0f + f[c];
-      a *= sc;
-      b = b * sc + f[p.C + c];
+  {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int c = threadIdx.x + it * 256;
+      if (c >= p.C) break;
+      const int g = c / cpg;
+      float a = s_rstd[g] * s_g[c];
+      float b = s_be[c] - s_mean[g] * a;
+      a *= f_sc[it];
+      b = b * f_sc[it] + f_sh[it];
+      s_a[c] = a; s_b[c] = b;
     }
-    s_a[c] = a; s_b[c] = b;
   }
   __syncthreads();
   const int vecs = p.C >> 3;
@@ -181,6 +194,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
     return o;
   };
   int r = r0 + rl;
+  for (; r + 7 * lanes < r1; r += 8 * lanes) {
+    uint4 raw[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) raw[u] = *reinterpret_cast<const uint4*>(xb + (long long)(r + u * lanes) * p.x_ld);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(yb + (long long)(r + u * lanes) * p.y_ld) = one(raw[u]);
+  }
   for (; r + 3 * lanes < r1; r += 4 * lanes) {
     uint4 raw[4];
 #pragma unroll

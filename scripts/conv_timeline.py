@@ -42,13 +42,18 @@ def run(N, H, W, Ci, Co, k, bn=0, iters=20, tag=""):
     d = dbg[:grid * 8].view(grid, 8).cpu().numpy().astype(np.float64)
     t0 = d[:, 0].min()
     start, setup, first, mma_end, acc, done = [(d[:, i] - t0) / 1e3 for i in range(6)]
+    epi_done = (d[:, 6] - t0) / 1e3
     kb = k * k * ((Ci + 63) // 64)
     print(f"--- {tag} N={N} {H}x{W} Cin={Ci} Cout={Co} k={k} | grid={grid} BN={info[1]} cg={info[4]} S={info[5]} stages={info[2]} smem={info[3]} kblocks={kb}")
     print(f"    {ms*1e3:8.1f} us/launch  {fl/ms/1e9:8.1f} TFLOP/s   kernel span {done.max():.1f} us")
     med = np.median
-    print(f"    per CTA (us, median): setup {med(setup-start):.2f} | wait first operands {med(first-setup):.2f} | "
-          f"mainloop {med(mma_end-first):.2f} ({med(mma_end-first)/kb*1e3:.0f} ns/kblock) | drain->acc {med(acc-mma_end):.2f} | "
-          f"epilogue {med(done-acc):.2f} | total {med(done-start):.2f}")
+    lead = d[:, 2] > 0          # in pair mode only the leader CTA issues MMAs (and stamps slots 2, 3)
+    staged = d[:, 6] > 0
+    print(f"    per CTA (us, median): setup {med(setup-start):.2f} | wait first operands {med((first-setup)[lead]):.2f} | "
+          f"mainloop {med((mma_end-first)[lead]):.2f} ({med((mma_end-first)[lead])/kb*1e3:.0f} ns/kblock) | "
+          f"drain->acc {med((acc-mma_end)[lead]):.2f} | epilogue {med(done-acc):.2f}"
+          + (f" (compute {med((epi_done-acc)[staged]):.2f}, store+teardown {med((done-epi_done)[staged]):.2f})" if staged.any() else "")
+          + f" | total {med(done-start):.2f}")
     order = np.argsort(start)
     waves = start[order]
     print(f"    CTA start times (us) pct 0/25/50/75/100: {np.percentile(start,[0,25,50,75,100]).round(1).tolist()}  "

@@ -1,11 +1,11 @@
 #!/bin/bash
-# GPU session 13: calibrated split-K; full suite + bench
+# GPU session 19: ncu --set full on the fused MLP, GroupNorm apply and window attention kernels (one forward, batch 16)
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/tests_all.log 2>&1
-timeout 300 python scripts/profile_ops.py 16 > gpurun_out/ops_b16.log 2>&1
-timeout 500 python bench.py > gpurun_out/bench.log 2>&1
-timeout 300 python bench.py --batch 1 --steps 5 --no-cpu-baseline > gpurun_out/bench_b1.log 2>&1
-tail -5 gpurun_out/tests_all.log
-head -20 gpurun_out/ops_b16.log
-grep -o '"ms_per_denoise_step": [0-9.]*' gpurun_out/bench.log gpurun_out/bench_b1.log
-grep -o '"value": [0-9.]*' gpurun_out/bench.log | head -3
+timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:mlp_fused -c 3 \
+    -o gpurun_out/prof_mlp -f python scripts/profile_forward.py --iters 1 > gpurun_out/ncu_mlp.log 2>&1
+timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gn_apply -c 12 \
+    -o gpurun_out/prof_gn -f python scripts/profile_forward.py --iters 1 > gpurun_out/ncu_gn.log 2>&1
+timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:window_attn -c 3 \
+    -o gpurun_out/prof_attn -f python scripts/profile_forward.py --iters 1 > gpurun_out/ncu_attn.log 2>&1
+tail -2 gpurun_out/ncu_mlp.log gpurun_out/ncu_gn.log gpurun_out/ncu_attn.log
+ls -la gpurun_out/*.ncu-rep
