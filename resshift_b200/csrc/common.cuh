@@ -140,6 +140,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// same arrival with the default (CTA-scope) release: no cluster-scope memory fence (~2000 cycles, profiles/r1_s21_*).
+// Sufficient when the data the arrival publishes is consumed inside the ARRIVING thread's own CTA (its tensor core
+// reading its own shared memory, made visible by fence.proxy.async) and the remote waiter only needs the count.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -256,6 +262,9 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // the staged shared memory has been READ by every committed store (it may be reused / the CTA may exit); the global
 // writes themselves complete asynchronously, at the latest at kernel completion
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (TMA store reads them)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -460,7 +460,7 @@ struct Builder {
       conv(a, b + ".attn.proj", 1, 1, Ed, &e, &e, ACT_NONE);              // x = shortcut + attn
       View n2 = P.make_view(x.N, x.H, x.W, Ed);
       gn(e, b + ".norm2", n2, 0, -1);
-      if (fuse_mlp && mlp_supported(Ed, hidden, x.H, x.W)) {
+      if (fuse_mlp && mlp_supported(Ed, hidden, x.H, x.W, x.N)) {
         mlp(n2, b + ".mlp", Ed, hidden, e, e);                            // x = x + fc2(gelu(fc1(n2))), one kernel
       } else {
         View f = P.make_view(x.N, x.H, x.W, hidden);

@@ -469,17 +469,19 @@ struct MlpDesc {
   int grid = 0; size_t smem = 0;
 };
 
-inline bool mlp_supported(int E, int Hd, int H, int W) {
+inline bool mlp_supported(int E, int Hd, int H, int W, int N) {
   bool fus = false;
-  conv_tile_slots(H, W, &fus);
-  return E % 64 == 0 && E <= 256 && Hd % kMlpHc == 0 && fus;
+  const int slots = conv_tile_slots(H, W, &fus);
+  const int bw = pow2_floor_div(W, kConvBM), bh = pow2_floor_div(H, kConvBM / bw), bn = kConvBM / (bw * bh);
+  const int tiles = slots * ((N + bn - 1) / bn);
+  return E % 64 == 0 && E <= 256 && Hd % kMlpHc == 0 && fus && tiles % 2 == 0;   // the kernel runs as CTA pairs
 }
 
 inline int mlp_finalize(MlpDesc& d) {
   MlpParams& p = d.prm;
   std::memset(&p, 0, sizeof(p));
   const int H = d.in.H, W = d.in.W, N = d.in.N;
-  RS_CHECK(mlp_supported(d.E, d.Hd, H, W), "fused MLP: unsupported shape");
+  RS_CHECK(mlp_supported(d.E, d.Hd, H, W, N), "fused MLP: unsupported shape (E % 64, E <= 256, hidden % 128, even tile count)");
   RS_CHECK(d.in.C == d.E && d.out.C == d.E, "fused MLP: channel mismatch");
   p.E = d.E; p.Hd = d.Hd; p.bias1 = d.b1; p.bias2 = d.b2;
   p.bw = pow2_floor_div(W, kConvBM);
@@ -488,32 +490,24 @@ inline int mlp_finalize(MlpDesc& d) {
   p.tiles_w = W / p.bw; p.tiles_h = H / p.bh;
   const int tiles_n = (N + p.bn - 1) / p.bn;
   p.Wout = W; p.Hout = H; p.Nimg = N;
-  // shared memory: X (E/64 tiles) + two H buffers + barriers + both bias vectors, the rest is weight ring slots:
-  // one hidden chunk of each stream (E/64 fc1 tiles, kMlpHc/64 fc2 tiles), spare slots to the fc1 ring first
-  const size_t kW1 = (size_t)kMlpHc * 128;
-  const size_t slot2 = (size_t)d.E * 128;
+  // shared memory per CTA: X (E/64 tiles) + two H buffers + barriers + both bias vectors; the rest is ring slots for
+  // this CTA's HALF of the weight tiles: two hidden chunks of the fc2 stream, everything else to the fc1 stream
+  const size_t kW1 = (size_t)(kMlpHc / 2) * 128;
+  const size_t slot2 = (size_t)(d.E / 2) * 128;
   const int kHT = kMlpHc / 64, kx = d.E / 64;
   const size_t fixed = (size_t)kx * 16384 + (size_t)2 * kHT * 16384 + 1024 + 512 + (size_t)(d.Hd + d.E) * sizeof(float);
   RS_CHECK(fixed + kHT * slot2 + (size_t)kx * kW1 <= 227 * 1024, "fused MLP: not enough shared memory for the weight rings");
   const size_t budget = 227 * 1024 - fixed;
-  p.ring2 = kHT;
+  p.ring2 = (int)std::min<size_t>(2 * kHT, (budget - (size_t)kx * kW1) / slot2);
   p.ring1 = (int)std::min<size_t>(12, (budget - (size_t)p.ring2 * slot2) / kW1);
-  {
-    const size_t spare = budget - (size_t)p.ring2 * slot2 - (size_t)p.ring1 * kW1;
-    p.ring2 += (int)std::min<size_t>(2, spare / slot2);
-  }
   p.has_res = d.has_res ? 1 : 0;
-  d.grid = p.tiles_w * p.tiles_h * tiles_n;
-  {
-    const int want = env_int("RS_MLP_CLUSTER", 4);
-    p.cluster = (want >= 4 && d.grid % 4 == 0 && kMlpHc % 32 == 0 && d.E % 32 == 0) ? 4 : ((want >= 2 && d.grid % 2 == 0) ? 2 : 1);
-  }
+  d.grid = p.tiles_w * p.tiles_h * tiles_n;      // even (mlp_supported): CTA pairs
   d.smem = fixed + (size_t)p.ring1 * kW1 + (size_t)p.ring2 * slot2;
   RS_CHECK(d.smem <= 227 * 1024, "fused MLP: shared memory budget exceeded");
   int rc = encode_act_map(&p.tmX, d.in.ptr, d.E, W, H, N, d.in.sW(), d.in.sH(), d.in.sN(), p.bw, p.bh, p.bn, 64);
   if (rc) return rc;
-  rc = encode_weight_map(&p.tmW1, d.w1, d.E, d.Hd, kMlpHc / p.cluster); if (rc) return rc;   // each CTA fetches 1/cluster of a tile
-  rc = encode_weight_map(&p.tmW2, d.w2, d.Hd, d.E, d.E / p.cluster); if (rc) return rc;
+  rc = encode_weight_map(&p.tmW1, d.w1, d.E, d.Hd, kMlpHc / 2); if (rc) return rc;   // each CTA of a pair fetches half a tile
+  rc = encode_weight_map(&p.tmW2, d.w2, d.Hd, d.E, d.E / 2); if (rc) return rc;
   rc = encode_act_map(&p.tmOut, d.out.ptr, d.E, W, H, N, d.out.sW(), d.out.sH(), d.out.sN(), p.bw, p.bh, p.bn, 64);
   if (rc) return rc;
   if (d.has_res) {
@@ -530,7 +524,7 @@ inline int mlp_finalize(MlpDesc& d) {
 }
 
 inline int mlp_launch(const MlpDesc& d, cudaStream_t st) {
-  (void)launch_kc(mlp_fused_sm100_kernel, dim3(d.grid), dim3(kMlpThreads), d.smem, st, d.prm.cluster, d.prm);
+  (void)launch_kc(mlp_fused_sm100_kernel, dim3(d.grid), dim3(kMlpThreads), d.smem, st, 2, d.prm);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }

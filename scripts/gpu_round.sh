@@ -1,11 +1,11 @@
 #!/bin/bash
-# GPU session 19: ncu --set full on the fused MLP, GroupNorm apply and window attention kernels (one forward, batch 16)
+# GPU session 25: warp-uniform control loops (elect-predicated tcgen05.mma / commit / TMA issue) in conv + MLP kernels
 mkdir -p gpurun_out
-timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:mlp_fused -c 3 \
-    -o gpurun_out/prof_mlp -f python scripts/profile_forward.py --iters 1 > gpurun_out/ncu_mlp.log 2>&1
-timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gn_apply -c 12 \
-    -o gpurun_out/prof_gn -f python scripts/profile_forward.py --iters 1 > gpurun_out/ncu_gn.log 2>&1
-timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:window_attn -c 3 \
-    -o gpurun_out/prof_attn -f python scripts/profile_forward.py --iters 1 > gpurun_out/ncu_attn.log 2>&1
-tail -2 gpurun_out/ncu_mlp.log gpurun_out/ncu_gn.log gpurun_out/ncu_attn.log
-ls -la gpurun_out/*.ncu-rep
+timeout 600 python -m pytest tests/test_gpu_ops.py -x -q 2>&1 | tail -5
+timeout 300 python scripts/mlp_timeline.py > gpurun_out/mlp_timeline.log 2>&1; tail -10 gpurun_out/mlp_timeline.log
+timeout 300 python scripts/mlp_timeline.py 16 8 8 2>&1 | head -1
+timeout 300 python scripts/mlp_timeline.py 16 32 32 2>&1 | head -1
+timeout 300 python scripts/conv_timeline.py > gpurun_out/conv_timeline.log 2>&1; cat gpurun_out/conv_timeline.log
+timeout 900 python -m pytest tests/test_gpu_unet.py -x -q 2>&1 | tail -5
+timeout 300 python scripts/profile_ops.py > gpurun_out/per_op.log 2>&1; head -40 gpurun_out/per_op.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b16.log 2> gpurun_out/bench_b16.err; cat gpurun_out/bench_b16.log | cut -c1-420

@@ -30,8 +30,8 @@ for _ in range(10):
 e1.record(); torch.cuda.synchronize()
 print(f"N={N} {H}x{W}: {e0.elapsed_time(e1)/10*1e3:.1f} us per launch")
 d = dbg.cpu().view(64, 8)
-print("chunk | MMA: acc1_empty ok, W1 landed, h_full ok, W2 landed | EPI: acc1_full, h_empty ok, gelu done, signalled   (cycles)")
-for j in range(63):
+print("chunk | MMA: GEMM1 start (acc1_empty ok), GEMM1 issued, h_full ok, GEMM2 issued | EPI: acc1_full, h_empty ok, gelu done, signalled   (cycles)")
+for j in range(62):
     if int(d[j].abs().sum()):
         print(j, d[j].tolist())
 print("final: acc2_full seen", int(d[63, 0]), " stores done", int(d[63, 1]))
