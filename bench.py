@@ -90,8 +90,12 @@ def cpu_reference_images_per_s(steps_T: int, n_images: int, repeats: int):
     from oracle import unet_oracle as uo
     from resshift_b200.config import preset
     from resshift_b200.weights import random_state_dict
-    # torch's default intra-op thread count (= the cores this process may use); forcing os.cpu_count() threads
-    # inside a cgroup-limited container oversubscribes and stalls
+    # torch's default intra-op thread count (= the physical cores this process may use); forcing os.cpu_count()
+    # threads inside a cgroup-limited container oversubscribes and stalls.  torchrun exports OMP_NUM_THREADS=1 to its
+    # workers, which would silently make this a single-thread baseline: undo that with half the schedulable CPUs
+    # (SMT pairs), the same count torch picks on its own.
+    if torch.get_num_threads() == 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        torch.set_num_threads(max(1, min(64, len(os.sched_getaffinity(0)) // 2)))
     ucfg, dcfg = preset("realsr_journal", steps_T)
     sd = random_state_dict(ucfg, 0)
     tabs = do.schedule_tables(do.eta_schedule(dcfg.steps, dcfg.min_noise_level, dcfg.etas_end, dcfg.kappa,

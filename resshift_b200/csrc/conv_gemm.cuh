@@ -77,6 +77,9 @@ struct ConvParams {
   int gn_cstride[2];
   int gn_coff[2];
   int gn_slots;
+  // persistent variant (conv_persist.cuh): CTAs (pairs) walk work units u = worker, worker + #workers, ...
+  int persist;
+  int num_units;         // (pixel tiles or tile pairs) x channel tiles
 };
 
 #ifdef __CUDACC__

@@ -36,7 +36,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("impl", ["tcgen05_cg1", "tcgen05_cg2", "tcgen05_msub2", "simt"])
+@pytest.mark.parametrize("impl", ["tcgen05_cg1", "tcgen05_cg2", "tcgen05_msub2", "tcgen05_persist_cg1", "tcgen05_persist_cg2", "simt"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv2d(case, impl):
     N, H, W, Ci, Co, k, s, bn = case
@@ -48,6 +48,9 @@ def test_conv2d(case, impl):
         os.environ["RS_CONV_CG"] = "1"         # one CTA per 128-pixel tile (tcgen05 cta_group::1)
     elif impl.endswith("cg2"):
         os.environ["RS_CONV_CG"] = "2"         # CTA pairs: 256-pixel tiles, tcgen05 cta_group::2, half of B per CTA
+    # persistent kernel (one CTA / pair per SM walking several tiles, double-buffered accumulators) forced on; off
+    # otherwise so that both kernels are covered whatever the cost model would pick
+    os.environ["RS_CONV_PERSIST"] = "1" if "persist" in impl else "0"
     try:
         g = torch.Generator(device="cuda").manual_seed(hash(case) % 1000)
         x = G.nhwc16(torch.randn(N, Ci, H, W, device="cuda", generator=g))
@@ -113,7 +116,8 @@ def test_conv2d_fused_groupnorm_statistics(case, msub):
     cstride, coff = Co + 32, 32
     outs, parts = [], []
     os.environ["RS_CONV_MSUB"] = "2" if msub.endswith("msub2") else "1"
-    os.environ["RS_CONV_CG"] = "2" if msub == "cg2" else "1"
+    os.environ["RS_CONV_CG"] = "2" if msub.endswith("cg2") else "1"
+    os.environ["RS_CONV_PERSIST"] = "1" if msub.startswith("persist") else "0"
     for rep in range(2):
         out = torch.empty(N, H, W, Co, dtype=torch.float16, device="cuda")
         part = torch.full((N * 64 * cstride * 2,), float("nan"), dtype=torch.float32, device="cuda")
@@ -126,6 +130,7 @@ def test_conv2d_fused_groupnorm_statistics(case, msub):
         parts.append(part[:N * slots.value * cstride * 2].view(N, slots.value, cstride, 2)[:, :, coff:coff + Co].clone())
     os.environ.pop("RS_CONV_MSUB", None)
     os.environ.pop("RS_CONV_CG", None)
+    os.environ.pop("RS_CONV_PERSIST", None)
     assert torch.equal(outs[0], outs[1]) and torch.equal(parts[0], parts[1])         # deterministic
     ref = G.ref_conv(x, w, b, residual=res)
     assert (G.nchw32(outs[0]) - ref).abs().max().item() <= _tol(ref)
@@ -137,6 +142,44 @@ def test_conv2d_fused_groupnorm_statistics(case, msub):
     assert not torch.isnan(parts[0]).any()
     assert (s_got - s_ref).abs().max().item() <= 1e-3 * (1 + s_ref.abs().max().item())
     assert (q_got - q_ref).abs().max().item() <= 1e-4 * q_ref.abs().max().item()
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("case", [(16, 64, 64, 160, 160, 3), (16, 64, 64, 192, 576, 1), (5, 64, 64, 96, 320, 3), (16, 32, 32, 64, 64, 3)])
+def test_conv2d_persistent_matches_one_tile_per_cta(case, cg):
+    """Many tiles per SM: the persistent kernel (tiles strided over one CTA / CTA pair per SM, TMEM double buffering,
+    epilogue overlapped with the next tile's main loop) must give bit-identical outputs and GroupNorm partials to the
+    one-tile-per-CTA kernel (same accumulation order), with a residual input and fused statistics."""
+    import ctypes as C
+    N, H, W, Ci, Co, k = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = G.nhwc16(torch.randn(N, Ci, H, W, device="cuda", generator=g))
+    w = torch.randn(Co, Ci, k, k, device="cuda", generator=g) / (Ci * k * k) ** 0.5
+    b = torch.randn(Co, device="cuda", generator=g)
+    res = G.nhwc16(torch.randn(N, Co, H, W, device="cuda", generator=g))
+    wp, ipad = G.pack_weight(w)
+    outs, parts = [], []
+    os.environ["RS_CONV_CG"] = str(cg)
+    try:
+        for persist in (0, 1, 1):
+            os.environ["RS_CONV_PERSIST"] = str(persist)
+            out = torch.full((N, H, W, Co), float("nan"), dtype=torch.float16, device="cuda")
+            part = torch.full((N * 64 * Co * 2,), float("nan"), dtype=torch.float32, device="cuda")
+            slots = C.c_int32()
+            _lib.check(G.L.rs_op_conv2d_stats(x.data_ptr(), N, H, W, Ci, Ci, wp.data_ptr(), ipad, b.data_ptr(), Co, k, 1,
+                                              res.data_ptr(), Co, out.data_ptr(), Co, 0, 0, part.data_ptr(), Co, 0,
+                                              C.byref(slots), G.stream()))
+            torch.cuda.synchronize()
+            outs.append(out)
+            parts.append(part[:N * slots.value * Co * 2].clone())
+    finally:
+        os.environ.pop("RS_CONV_CG", None)
+        os.environ.pop("RS_CONV_PERSIST", None)
+    assert not torch.isnan(outs[1].float()).any() and not torch.isnan(parts[1]).any()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    assert torch.equal(parts[0], parts[1]) and torch.equal(parts[1], parts[2])
+    ref = G.ref_conv(x, w, b, residual=res)
+    assert (G.nchw32(outs[1]) - ref).abs().max().item() <= _tol(ref)
 
 
 @pytest.mark.parametrize("force", [0, 2, 4])
