@@ -82,6 +82,9 @@ def log(msg):
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
+NCU_DRAM_BYTES_PER_GEMM_LAUNCH = 22.67e6
+
+
 def cpu_reference_images_per_s(steps_T: int, n_images: int, repeats: int):
     """The reference's algorithm for this path on the host cores: the CPU oracle (a torch fp32 restatement of
     UNetModelSwin.forward + p_sample, pinned to reference-generated goldens), all host threads."""
@@ -273,13 +276,26 @@ def run_gpu(args):
     peaks = _peaks()
     conv_tflops = flops.value / (pk[0] * 1e-3) / 1e12 if pk[0] > 0 else 0.0
     roofline = {
-        "kernel": "conv_gemm_sm100_kernel (all conv3x3 / conv1x1 / linear layers)", "bound": "tensor",
+        "kernel": "tcgen05 GEMM kernels: conv_gemm_sm100_kernel<1|2>, conv_gemm_persist_sm100_kernel<1|2> (all conv3x3 / "
+                  "conv1x1 / linear layers) + mlp_fused_sm100_kernel (Swin MLPs)", "bound": "tensor",
         "achieved": conv_tflops, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
-        "frac": conv_tflops / peaks["tensor_tflops"], "traffic": None,
+        "frac": conv_tflops / peaks["tensor_tflops"],
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 30 GEMM launches of the 64x64 level
+        # captured with `ncu --set full` on this workload (cold caches: ncu flushes between replays);
+        # profiles/r1_s31_gemm_kernels_ncu_full_summary.csv.  Reads are ~ each layer's input (+ residual) once — e.g.
+        # 34.9 MB for a 64x64 160->160 3x3 layer whose input + residual + weights are 42.4 MB (part still L2-resident) —
+        # i.e. no operand is re-read from DRAM (tap / channel-tile re-use is served by the 126 MB L2); outputs mostly
+        # stay in L2 (writes ~1 MB / launch).
+        "traffic": NCU_DRAM_BYTES_PER_GEMM_LAUNCH if B == BATCH_PER_GPU else None,
         "launches_per_forward": int(nconv.value), "avg_launch_us": pk[0] * 1e3 / max(1, nconv.value),
         "algorithmic_gflop_per_forward": flops.value / 1e9, "peak_source": peaks["source"],
         "per_forward_ms_by_kernel": {"conv_gemm": pk[0], "groupnorm": pk[1], "window_attn": pk[2], "upsample": pk[3]},
-        "note": "events around each launch of one un-graphed forward (includes launch gaps)",
+        "traffic_source": "profiles/r1_s31_gemm_kernels_ncu_full_summary.csv (ncu --set full, 30 launches, batch 16)",
+        "tensor_pipe_active_pct_ncu": {"conv_gemm_persist<2> (3x3, 64x64)": 54.0, "conv_gemm<2>": 47.0, "mlp_fused": 23.6,
+                                       "conv_gemm_persist<1> (1x1, epilogue-bound)": 13.3, "conv_gemm<1>": 12.7},
+        "note": "achieved = algorithmic FLOPs of all GEMM launches / sum of their durations, CUDA events around every "
+                "launch of one un-graphed forward on the launching stream (includes inter-launch gaps, so it "
+                "under-states the graph-replayed step)",
     }
     # whole-step tensor-pipe fraction as a cross-check
     step_tflops = world * B * T * GF_PER_IMAGE_STEP / (ms_per_step * 1e-3) / 1e12 / world

@@ -331,6 +331,10 @@ struct Builder {
   struct Writer { long long off; int C; int list; int op; };
   std::map<int, std::vector<Writer>> writers;      // tensor id -> latest conv writers by channel range
   const bool fuse_mlp = env_int("RS_MLP_FUSE", 1) && !env_is("RS_CONV_IMPL", "simt");
+  // norm2 applied inside the fused MLP kernel: implemented and bit-identical, but OFF by default — every (non-persistent)
+  // MLP CTA re-derives the affine from the partial sums before its first MMA, which costs more than the gn_apply launch it
+  // saves (64x64: +21 us vs -16 us, profiles/r1_s32_*); needs a persistent MLP kernel or a finalize pass to pay off
+  const bool fuse_mlp_norm = env_int("RS_MLP_NORM_FUSE", 0) != 0;
   const bool fuse_stats = env_int("RS_GN_FUSE", 1) && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt");
   Builder(rs_plan& p) : P(p), E(*p.e), cur(&p.ops) {}
   int list_id() const { return cur == &P.fe_ops ? 0 : 1; }
@@ -403,20 +407,52 @@ struct Builder {
     P.touch(qkv, i); P.touch(out, i);
     cur->push_back(op);
   }
-  void mlp(const View& in, const std::string& name, int E, int Hd, const View& out, const View& res) {
+  // producers of every channel of `in` whose epilogues can deliver GroupNorm statistics (empty: not fusable)
+  std::vector<Writer> stat_producers(const View& in) {
+    bool fusable = false;
+    conv_tile_slots(in.H, in.W, &fusable);
+    std::vector<Writer> prod;
+    if (fuse_stats && fusable) {
+      int covered = 0;
+      auto it = writers.find(in.tens);
+      if (it != writers.end())
+        for (const Writer& w : it->second)
+          if (w.off >= in.off && w.off + w.C <= in.off + in.C) { prod.push_back(w); covered += w.C; }
+      bool ok = covered == in.C;
+      for (const Writer& w : prod) ok = ok && list(w.list)[w.op].stat_dst.size() < 2;
+      if (!ok) prod.clear();
+    }
+    return prod;
+  }
+  // norm_name non-empty: `in` is the un-normalised tensor and the kernel applies that GroupNorm to its X tile itself
+  // (returns false, adding nothing, when the statistics cannot come from the producers' epilogues)
+  bool mlp(const View& in, const std::string& name, int E, int Hd, const View& out, const View& res,
+           const std::string& norm_name = std::string()) {
     Op op; op.kind = OP_MLP;
     op.mlp.in = in; op.mlp.out = out; op.mlp.res = res; op.mlp.has_res = true; op.mlp.E = E; op.mlp.Hd = Hd;
     op.w_name = name + ".fc1.weight"; op.b_name = name + ".fc1.bias";
     op.w2_name = name + ".fc2.weight"; op.b2_name = name + ".fc2.bias";
+    std::vector<Writer> prod;
+    if (!norm_name.empty()) {
+      prod = stat_producers(in);
+      if (prod.empty() || Hd < 4 * E) return false;
+      op.g_name = norm_name;
+      op.gn.in = in; op.gn.fused = true; op.gn.slots = conv_tile_slots(in.H, in.W);
+      op.stats_off = stats_off;
+      stats_off += align_up((size_t)in.N * op.gn.slots * in.C * 2 * sizeof(float), 256);
+    }
     const int i = opi();
     P.touch(in, i); P.touch(out, i); P.touch(res, i);
     cur->push_back(op);
+    for (const Writer& w : prod)
+      list(w.list)[w.op].stat_dst.push_back({list_id(), (int)cur->size() - 1, (int)(w.off - in.off)});
     if (out.tens >= 0) {
       auto& ws = writers[out.tens];
       ws.erase(std::remove_if(ws.begin(), ws.end(), [&](const Writer& w) {
                  return w.off < out.off + E && out.off < w.off + w.C; }), ws.end());
       ws.push_back({out.off, E, list_id(), (int)cur->size() - 1});
     }
+    return true;
   }
   void upsample(const View& in, const View& out) {
     Op op; op.kind = OP_UPSAMPLE; op.u_in = in; op.u_out = out;
@@ -458,9 +494,12 @@ struct Builder {
       View a = P.make_view(x.N, x.H, x.W, Ed);
       attn(qkv, a, b, (i % 2) ? shift_odd : 0);
       conv(a, b + ".attn.proj", 1, 1, Ed, &e, &e, ACT_NONE);              // x = shortcut + attn
+      const bool mlp_ok = fuse_mlp && mlp_supported(Ed, hidden, x.H, x.W, x.N);
+      // x = x + fc2(gelu(fc1(norm2(x)))) in one kernel, norm2 applied to the X tile in shared memory
+      if (mlp_ok && fuse_mlp_norm && mlp(e, b + ".mlp", Ed, hidden, e, e, b + ".norm2")) continue;
       View n2 = P.make_view(x.N, x.H, x.W, Ed);
       gn(e, b + ".norm2", n2, 0, -1);
-      if (fuse_mlp && mlp_supported(Ed, hidden, x.H, x.W, x.N)) {
+      if (mlp_ok) {
         mlp(n2, b + ".mlp", Ed, hidden, e, e);                            // x = x + fc2(gelu(fc1(n2))), one kernel
       } else {
         View f = P.make_view(x.N, x.H, x.W, hidden);
@@ -683,6 +722,12 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       RS_CHECK(m.w1 && m.w2 && m.b1 && m.b2, "missing MLP parameters " + op.w_name);
       const Param* w1p = E.find(op.w_name); const Param* w2p = E.find(op.w2_name);
       RS_CHECK(w1p->ipad == m.E && w2p->ipad == m.Hd, "MLP weight padding");
+      if (!op.g_name.empty()) {
+        m.gn_in_part = reinterpret_cast<const float*>(P.ws + P.off_stats + op.stats_off);
+        m.gn_in_slots = op.gn.slots;
+        m.gn_in_gamma = E.at<float>(op.g_name + ".weight"); m.gn_in_beta = E.at<float>(op.g_name + ".bias");
+        RS_CHECK(m.gn_in_gamma && m.gn_in_beta, "missing GroupNorm parameters " + op.g_name);
+      }
       for (int i = 0; i < 2; ++i) {
         m.gn_part[i] = nullptr;
         if (i < (int)op.stat_dst.size()) {

@@ -508,9 +508,18 @@ inline int gn_launch(const GnDesc& g, cudaStream_t st) {
   int actas = std::max(1, std::min((HW + 15) / 16, (148 * 4 + N - 1) / N));
   const int arows = (HW + actas - 1) / actas;
   actas = (HW + arows - 1) / arows;
+  // small tensors: split the channels too (slices aligned to GroupNorm groups and to 8-channel vectors) until there
+  // are ~1.5 CTAs per SM — a 8x8 C=640 layer would otherwise run on 64 CTAs
+  int csplit = 1;
+  {
+    const int cpg = C / 32;
+    int unit = cpg; while (unit % 8) unit += cpg;                   // lcm(8, channels per group)
+    for (int cs = 2; actas * N * csplit < 222 && cs <= C / unit; ++cs)
+      if (C % cs == 0 && (C / cs) % unit == 0) csplit = cs;
+  }
   GnApplyParams ap{g.in.ptr, g.in.sN(), g.in.ld, g.out.ptr, g.out.sN(), g.out.ld, C, HW, N, g.part, slots,
-                   g.gamma, g.beta, g.film, g.film_sN, g.silu, arows, 1e-5f};
-  (void)launch_k(gn_apply_kernel, dim3(actas, N), dim3(256), (size_t)(4 * C + 64) * sizeof(float), st, ap);
+                   g.gamma, g.beta, g.film, g.film_sN, g.silu, arows, 1e-5f, C / csplit};
+  (void)launch_k(gn_apply_kernel, dim3(actas, N, csplit), dim3(256), (size_t)(4 * (C / csplit) + 64) * sizeof(float), st, ap);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -526,6 +535,9 @@ struct MlpDesc {
   int gn_cstride[2] = {0, 0};
   int gn_coff[2] = {0, 0};
   long long* dbg = nullptr;
+  // optional fused input GroupNorm (plain affine): `in` is then the un-normalised tensor
+  const float* gn_in_part = nullptr; int gn_in_slots = 0;
+  const float* gn_in_gamma = nullptr; const float* gn_in_beta = nullptr;
   MlpParams prm;
   int grid = 0; size_t smem = 0;
 };
@@ -556,7 +568,8 @@ inline int mlp_finalize(MlpDesc& d) {
   const size_t kW1 = (size_t)(kMlpHc / 2) * 128;
   const size_t slot2 = (size_t)(d.E / 2) * 128;
   const int kHT = kMlpHc / 64, kx = d.E / 64;
-  const size_t fixed = (size_t)kx * 16384 + (size_t)2 * kHT * 16384 + 1024 + 512 + (size_t)(d.Hd + d.E) * sizeof(float);
+  const size_t fixed = (size_t)kx * 16384 + (size_t)2 * kHT * 16384 + 1024 + 512 + (size_t)(d.Hd + d.E) * sizeof(float) +
+                       (size_t)(2 * d.E * 2 + 2 * 32 * 2) * sizeof(float);   // + input-GN affine / group statistics
   RS_CHECK(fixed + kHT * slot2 + (size_t)kx * kW1 <= 227 * 1024, "fused MLP: not enough shared memory for the weight rings");
   const size_t budget = 227 * 1024 - fixed;
   p.ring2 = (int)std::min<size_t>(2 * kHT, (budget - (size_t)kx * kW1) / slot2);
@@ -576,6 +589,10 @@ inline int mlp_finalize(MlpDesc& d) {
     if (rc) return rc;
   }
   p.dbg = d.dbg;
+  p.gn_in_part = d.gn_in_part; p.gn_in_slots = d.gn_in_slots; p.gn_in_gamma = d.gn_in_gamma; p.gn_in_beta = d.gn_in_beta;
+  p.gn_in_eps = 1e-5f;
+  RS_CHECK(!d.gn_in_part || (d.gn_in_gamma && d.gn_in_beta && d.Hd >= 4 * d.E && d.E % 32 == 0 && d.gn_in_slots == p.tiles_w * p.tiles_h),
+           "fused MLP: input GroupNorm arguments");
   p.gn_slots = p.tiles_w * p.tiles_h;
   for (int i = 0; i < 2; ++i) { p.gn_part[i] = d.gn_part[i]; p.gn_cstride[i] = d.gn_cstride[i]; p.gn_coff[i] = d.gn_coff[i]; }
   if (p.gn_part[0] == nullptr && p.gn_part[1] != nullptr) {

@@ -42,6 +42,15 @@ struct MlpParams {
   int has_res;
   float* gn_part[2]; int gn_cstride[2]; int gn_coff[2]; int gn_slots;
   long long* dbg;                    // optional: CTA 0 writes a clock64 timeline [64 chunks][8] (profiling aid)
+  // optional fused input GroupNorm (the Swin block's norm2, models/swin_transformer.py:279): X is then the UN-normalised
+  // tensor and the CTA applies  a*x + b  (per image, per channel; plain affine, no FiLM / SiLU) to its X tile in
+  // shared memory before the first GEMM — one gn_apply launch and one activation round trip less per Swin block.
+  // Statistics arrive as the producer's deterministic partial sums, exactly as gn_apply_kernel reads them.
+  const float* gn_in_part;           // [N][gn_in_slots][E][2] or nullptr
+  int gn_in_slots;
+  const float* gn_in_gamma;          // [E]
+  const float* gn_in_beta;           // [E]
+  float gn_in_eps;
 };
 
 #ifdef __CUDACC__
@@ -71,9 +80,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
   uint64_t* h_empty = h_full + 2;                  // [2] per CTA (multicast commit)
   uint64_t* acc2_full = h_empty + 2;               // per CTA (multicast commit)
   uint64_t* res_bar = acc2_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  uint64_t* x_ready = res_bar + 1;                 // leader's: X tiles of both CTAs normalised in place (fused input GN)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
   float* s_b1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [Hd] fc1 bias
   float* s_b2 = s_b1 + p.Hd;                                                          // [E]  fc2 bias
+  float* s_ab = s_b2 + p.E;                                                           // [2 images][E][2] input-GN affine, [2][32][2] mean / rstd
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
@@ -97,7 +108,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
       mbar_init(&acc1_full[b], 1); mbar_init(&h_empty[b], 1);                                 // tcgen05.commit
       mbar_init(&acc1_empty[b], 2 * kMlpEpiWarps); mbar_init(&h_full[b], 2 * kMlpEpiWarps);   // GELU warps of both CTAs
     }
-    mbar_init(acc2_full, 1); mbar_init(res_bar, 1);
+    mbar_init(acc2_full, 1); mbar_init(res_bar, 1); mbar_init(x_ready, 2 * kMlpEpiWarps);
     mbar_fence_init();
   }
   if (warp == kMlpMmaWarp) { tmem_alloc_dyn_cg2(tmem_slot, 512u); tmem_relinquish_cg2(); }
@@ -117,8 +128,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
     const bool el = elect_one();
     const uint32_t lead_x = mapa_u32(smem_u32(x_full), 0);
     if (el) {
-      if (rank == 0) mbar_arrive_expect_tx(x_full, (uint32_t)(2 * kx * kTile));
-      for (int kb = 0; kb < kx; ++kb) tma_load_4d_cg2(sX + (size_t)kb * kTile, &p.tmX, lead_x, kb * kConvBK, w0, h0, n0);
+      if (p.gn_in_part) {
+        // fused input GroupNorm: each CTA's GELU warps wait for their OWN tile, normalise it, then signal the leader
+        mbar_arrive_expect_tx(x_full, (uint32_t)(kx * kTile));
+        for (int kb = 0; kb < kx; ++kb) tma_load_4d(sX + (size_t)kb * kTile, &p.tmX, x_full, kb * kConvBK, w0, h0, n0);
+      } else {
+        if (rank == 0) mbar_arrive_expect_tx(x_full, (uint32_t)(2 * kx * kTile));
+        for (int kb = 0; kb < kx; ++kb) tma_load_4d_cg2(sX + (size_t)kb * kTile, &p.tmX, lead_x, kb * kConvBK, w0, h0, n0);
+      }
     }
     int st1 = 0; uint32_t ph1 = 0;
     const int row0 = (int)rank * (kMlpHc / 2);
@@ -180,7 +197,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
         }
         if (dbg && el) dbg[c * 8 + 1] = clock64() - t_start;
       };
-      mbar_wait(x_full, 0);
+      mbar_wait(p.gn_in_part ? x_ready : x_full, 0);
+      tc_fence_after();
       gemm1(0);
       if (chunks > 1) gemm1(1);
       for (int j = 0; j < chunks; ++j) {
@@ -218,6 +236,83 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
     const int r = quad * 32 + lane;
     const int etid = threadIdx.x;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    if (p.gn_in_part) {
+      // ---- fused input GroupNorm: statistics -> per-(image, channel) affine -> X tile normalised in place ----
+      // (same arithmetic and summation order as gn_apply_kernel, so the operand equals what the separate pass stored)
+      const int E = p.E, cpg = E / 32;
+      const int nimg = p.bn;                                       // images this tile touches (1 or 2)
+      float* s_sum = s_b1;                                         // scratch [2][E][2] (bias1 is loaded afterwards)
+      float* s_mr = s_ab + 2 * E * 2;                              // [2][32][2]
+      for (int idx = etid; idx < nimg * E; idx += 32 * kMlpEpiWarps) {
+        const int img = idx / E, c = idx - img * E;
+        float sv = 0.f, qv = 0.f;
+        if (n0 + img < p.Nimg) {
+          const float* part = p.gn_in_part + (size_t)(n0 + img) * p.gn_in_slots * E * 2;
+          int sl = 0;
+          for (; sl + 16 <= p.gn_in_slots; sl += 16) {
+            float2 e[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) e[u] = *reinterpret_cast<const float2*>(part + ((size_t)(sl + u) * E + c) * 2);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { sv += e[u].x; qv += e[u].y; }
+          }
+          for (; sl + 4 <= p.gn_in_slots; sl += 4) {
+            float2 e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) e[u] = *reinterpret_cast<const float2*>(part + ((size_t)(sl + u) * E + c) * 2);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { sv += e[u].x; qv += e[u].y; }
+          }
+          for (; sl < p.gn_in_slots; ++sl) {
+            const float2 e = *reinterpret_cast<const float2*>(part + ((size_t)sl * E + c) * 2);
+            sv += e.x; qv += e.y;
+          }
+        }
+        s_sum[(img * E + c) * 2] = sv; s_sum[(img * E + c) * 2 + 1] = qv;
+      }
+      named_bar_sync(1, 32 * kMlpEpiWarps);
+      if (etid < 32 * nimg) {
+        const int img = etid >> 5, g = etid & 31;
+        float sv = 0.f, qv = 0.f;
+        for (int j = 0; j < cpg; ++j) { sv += s_sum[(img * E + g * cpg + j) * 2]; qv += s_sum[(img * E + g * cpg + j) * 2 + 1]; }
+        const float inv_cnt = 1.0f / (float)((long long)cpg * p.Hout * p.Wout);
+        const float mean = sv * inv_cnt;
+        const float var = fmaxf(qv * inv_cnt - mean * mean, 0.f);
+        s_mr[(img * 32 + g) * 2] = mean; s_mr[(img * 32 + g) * 2 + 1] = rsqrtf(var + p.gn_in_eps);
+      }
+      named_bar_sync(1, 32 * kMlpEpiWarps);
+      for (int idx = etid; idx < nimg * E; idx += 32 * kMlpEpiWarps) {
+        const int img = idx / E, c = idx - img * E, g = c / cpg;
+        const float a = s_mr[(img * 32 + g) * 2 + 1] * __ldg(p.gn_in_gamma + c);
+        const float b = __ldg(p.gn_in_beta + c) - s_mr[(img * 32 + g) * 2] * a;
+        s_ab[(img * E + c) * 2] = a; s_ab[(img * E + c) * 2 + 1] = b;
+      }
+      named_bar_sync(1, 32 * kMlpEpiWarps);
+      mbar_wait(x_full, 0);                                         // this CTA's X tile has landed
+      // in place: 128 rows x kx x eight 16-byte units (8 channels each); unit u of row rr sits at (u ^ (rr & 7))
+      const int rows_per_img = p.bw * p.bh;                         // bn == 2: rows 0..63 -> image n0, 64..127 -> n0 + 1
+      for (int idx = etid; idx < kx * kConvBM * 8; idx += 32 * kMlpEpiWarps) {
+        const int kb = idx / (kConvBM * 8), rem = idx - kb * (kConvBM * 8);
+        const int rr = rem >> 3, us = rem & 7;
+        const int ch = kb * 64 + ((us ^ (rr & 7)) << 3);
+        const float* ab = s_ab + ((size_t)(nimg == 2 && rr >= rows_per_img ? E : 0) + ch) * 2;
+        uint4* ptr = reinterpret_cast<uint4*>(sX + (size_t)kb * kTile + rr * 128 + us * 16);
+        uint4 raw = *ptr;
+        __half2* hh = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __half22float2(hh[j]);
+          f.x = fmaf(f.x, ab[(2 * j) * 2], ab[(2 * j) * 2 + 1]);
+          f.y = fmaf(f.y, ab[(2 * j + 1) * 2], ab[(2 * j + 1) * 2 + 1]);
+          hh[j] = __floats2half2_rn(f.x, f.y);
+        }
+        *ptr = raw;
+      }
+      fence_proxy_async_smem();                                     // the tensor core reads X through the async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(x_ready), 0));
+      named_bar_sync(1, 32 * kMlpEpiWarps);                         // s_sum (aliasing the bias area) is free again
+    }
     for (int i = etid; i < p.Hd; i += 32 * kMlpEpiWarps) s_b1[i] = __ldg(p.bias1 + i);
     for (int i = etid; i < p.E; i += 32 * kMlpEpiWarps) s_b2[i] = __ldg(p.bias2 + i);
     named_bar_sync(1, 32 * kMlpEpiWarps);

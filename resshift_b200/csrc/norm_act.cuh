@@ -38,6 +38,8 @@ struct GnApplyParams {
   int silu;
   int rows_per_cta;
   float eps;
+  int Cs;                   // channels per CTA (blockIdx.z selects the slice; a multiple of 8 and of C/32): small tensors
+                            // are split over channels as well as rows so that every SM gets a CTA
 };
 
 #ifdef __CUDACC__
@@ -101,33 +103,44 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const GnStatsParams p) {
 
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p) {
   pdl_trigger();
-  extern __shared__ float s_ab[];    // a[C], b[C], gamma[C], beta[C], mean[32], rstd[32]
+  extern __shared__ float s_ab[];    // a[Cs], b[Cs], gamma[Cs], beta[Cs], mean[32], rstd[32]  (this CTA's channel slice)
+  const int Cs = p.Cs;
+  const int c0 = blockIdx.z * Cs;    // first channel of the slice (group aligned)
   float* s_a = s_ab;
-  float* s_b = s_ab + p.C;
-  float* s_g = s_ab + 2 * p.C;
-  float* s_be = s_ab + 3 * p.C;
-  float* s_mean = s_ab + 4 * p.C;
+  float* s_b = s_ab + Cs;
+  float* s_g = s_ab + 2 * Cs;
+  float* s_be = s_ab + 3 * Cs;
+  float* s_mean = s_ab + 4 * Cs;
   float* s_rstd = s_mean + 32;
   const int n = blockIdx.y;
   const int cpg = p.C / 32;
   // layer parameters do not depend on the producing kernel: fetch them while it drains
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) { s_g[c] = __ldg(p.gamma + c); s_be[c] = __ldg(p.beta + c); }
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) { s_g[c] = __ldg(p.gamma + c0 + c); s_be[c] = __ldg(p.beta + c0 + c); }
   pdl_wait();
   // per-channel totals over the slots (independent loads, fixed order), staged in s_a / s_b together with the FiLM
   // pair (kept in registers: a thread owns the same channels in both passes); then per-group mean / rstd in a fixed
   // order over the group's channels
   float f_sc[8], f_sh[8];            // C <= 2048 -> at most 8 channels per thread
   {
-    const float* part = p.part + (size_t)n * p.slots * p.C * 2;
-    const float* f = p.film ? p.film + n * p.film_sN : nullptr;
+    const float* part = p.part + (size_t)n * p.slots * p.C * 2 + (size_t)c0 * 2;
+    const float* f = p.film ? p.film + n * p.film_sN + c0 : nullptr;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int c = threadIdx.x + it * 256;
-      if (c >= p.C) break;
+      if (c >= Cs) break;
       f_sc[it] = f ? 1.0f + f[c] : 1.0f;
       f_sh[it] = f ? f[p.C + c] : 0.0f;
       float s = 0.f, q = 0.f;
       int sl = 0;
+      // 16 independent loads in flight per thread (a 64x64 layer has 32 slots: two round trips instead of eight —
+      // this dependent chain, not bandwidth, is what the small GroupNorm launches wait for); summed in slot order
+      for (; sl + 16 <= p.slots; sl += 16) {
+        float2 e[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) e[u] = *reinterpret_cast<const float2*>(part + ((size_t)(sl + u) * p.C + c) * 2);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { s += e[u].x; q += e[u].y; }
+      }
       for (; sl + 4 <= p.slots; sl += 4) {
         float2 e[4];
 #pragma unroll
@@ -142,8 +155,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p)
       s_a[c] = s; s_b[c] = q;
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-      const int g = threadIdx.x;
+    if (threadIdx.x < Cs / cpg) {
+      const int g = threadIdx.x;         // group index inside the slice
       float s = 0.f, q = 0.f;
       for (int j = 0; j < cpg; ++j) { s += s_a[g * cpg + j]; q += s_b[g * cpg + j]; }
       const float inv_cnt = 1.0f / (float)((long long)cpg * p.HW);
@@ -157,7 +170,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p)
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int c = threadIdx.x + it * 256;
-      if (c >= p.C) break;
+      if (c >= Cs) break;
       const int g = c / cpg;
       float a = s_rstd[g] * s_g[c];
       float b = s_be[c] - s_mean[g] * a;
@@ -167,7 +180,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p)
     }
   }
   __syncthreads();
-  const int vecs = p.C >> 3;
+  const int vecs = Cs >> 3;
   const int lanes = blockDim.x / vecs;
   const int vec = threadIdx.x % vecs, rl = threadIdx.x / vecs;
   if (rl >= lanes) return;
@@ -177,8 +190,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p)
   for (int j = 0; j < 8; ++j) { a[j] = s_a[c + j]; b[j] = s_b[c + j]; }
   const int r0 = blockIdx.x * p.rows_per_cta;
   const int r1 = min(r0 + p.rows_per_cta, p.HW);
-  const __half* xb = p.x + n * p.x_sN + c;
-  __half* yb = p.y + n * p.y_sN + c;
+  const __half* xb = p.x + n * p.x_sN + c0 + c;
+  __half* yb = p.y + n * p.y_sN + c0 + c;
   auto one = [&](const uint4& raw) {
     const __half2* h = reinterpret_cast<const __half2*>(&raw);
     uint4 o;

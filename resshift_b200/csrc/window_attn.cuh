@@ -111,12 +111,20 @@ __global__ void __launch_bounds__(128) window_attn_kernel(const WinAttnParams p)
   for (int hi = 0; hi < p.hpc; ++hi) {
     const int head = head0 + hi;
     const int buf = hi & 1;
+    // this lane's 32 relative-position-bias values (a load-time table, independent of the staged q/k/v): issued before
+    // waiting for the tile so the L2 round trip hides under the cp.async wait and the QK^T MMAs
+    const float* bias = p.bias + (long long)head * 64 * 64;
+    float2 bv0[8], bv1[8];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      bv0[nt] = __ldg(reinterpret_cast<const float2*>(bias + row0 * 64 + nt * 8 + 2 * t));
+      bv1[nt] = __ldg(reinterpret_cast<const float2*>(bias + (row0 + 8) * 64 + nt * 8 + 2 * t));
+    }
     if (hi + 1 < p.hpc) { stage_head(head + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
     const __half* sQ = sbuf + buf * buf_halves;
     const __half* sK = sQ + 64 * kAttnPad;
     const __half* sV = sK + 64 * kAttnPad;
-    const float* bias = p.bias + (long long)head * 64 * 64;
 
     // S = Q K^T : Q fragments for the two k-steps (d 0..15, 16..31)
     uint32_t qa[2][4];
@@ -146,8 +154,7 @@ __global__ void __launch_bounds__(128) window_attn_kernel(const WinAttnParams p)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int col = nt * 8 + 2 * t;
-      const float2 b0 = *reinterpret_cast<const float2*>(bias + row0 * 64 + col);
-      const float2 b1 = *reinterpret_cast<const float2*>(bias + (row0 + 8) * 64 + col);
+      const float2 b0 = bv0[nt], b1 = bv1[nt];
       float m0 = 0.f, m1 = 0.f;
       if (p.shift) {
         if (swin_label(wy, col & 7, p.H, p.shift) != la) m0 = -100.0f;

@@ -74,6 +74,26 @@ def test_forward_blocks_vs_golden(golden_dir):
         os.environ.pop("RS_NO_REUSE", None)
 
 
+def test_norm2_fused_into_mlp_is_bit_identical_to_separate_groupnorm():
+    """The fused Swin MLP kernel applying norm2 to its X tile in shared memory (default) must reproduce, bit for bit,
+    the plan that runs gn_apply_kernel first (RS_MLP_NORM_FUSE=0): same partial sums, same affine, same rounding."""
+    outs = []
+    for fuse in ("1", "0"):
+        os.environ["RS_MLP_NORM_FUSE"] = fuse
+        try:
+            ucfg, _, m = _model("realsr")
+            g = torch.Generator(device="cuda").manual_seed(7)
+            x = torch.randn(3, 3, 64, 64, device="cuda", generator=g)
+            lq = torch.rand(3, 3, 64, 64, device="cuda", generator=g) * 2 - 1
+            t = torch.tensor([2, 9, 14], device="cuda")
+            outs.append((m(x, t, lq=lq).clone(), m.num_launches(3, 64, 64)))
+            del m
+        finally:
+            os.environ.pop("RS_MLP_NORM_FUSE", None)
+    assert outs[0][1] == outs[1][1] - 18, (outs[0][1], outs[1][1])      # one launch less per Swin block
+    assert not torch.isnan(outs[0][0]).any() and torch.equal(outs[0][0], outs[1][0])
+
+
 def test_forward_vs_oracle_fresh_inputs():
     """Oracle on new seeded inputs (not in the goldens), batch 3 with distinct timesteps."""
     from oracle import unet_oracle as uo
