@@ -1,6 +1,6 @@
 #!/bin/bash
-# GPU session 32: norm2 fused into the MLP kernel, channel-split GroupNorm apply for small tensors
+# GPU session 33: gn_apply with the first row batch in flight during the statistics prologue
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_unet.py -x -q 2>&1 | tail -6
-timeout 300 python scripts/profile_ops.py > gpurun_out/per_op.log 2>&1; grep -E "ops |gn |mlp" gpurun_out/per_op.log | head -24
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_unet.py -x -q 2>&1 | tail -4
+timeout 300 python scripts/profile_ops.py > gpurun_out/per_op.log 2>&1; grep -E "ops |gn " gpurun_out/per_op.log | head -20
 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b16.log 2> gpurun_out/bench_b16.err; cat gpurun_out/bench_b16.log | cut -c1-420
