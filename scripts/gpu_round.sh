@@ -1,6 +1,7 @@
 #!/bin/bash
-# GPU session 33: gn_apply with the first row batch in flight during the statistics prologue
+# GPU session 34: full GPU suite (incl. full-size faceir / inpaint parity), smoke(), bench lines (own arm + reference arm)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_unet.py -x -q 2>&1 | tail -4
-timeout 300 python scripts/profile_ops.py > gpurun_out/per_op.log 2>&1; grep -E "ops |gn " gpurun_out/per_op.log | head -20
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b16.log 2> gpurun_out/bench_b16.err; cat gpurun_out/bench_b16.log | cut -c1-420
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+timeout 900 python bench.py > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err; cat gpurun_out/bench_default.log | cut -c1-300
+timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.log | cut -c1-400

@@ -109,6 +109,26 @@ def test_forward_vs_oracle_fresh_inputs():
     assert mx <= FWD_MAX and mn <= FWD_MEAN
 
 
+@pytest.mark.parametrize("name", ["faceir", "inpaint"])
+def test_forward_full_size_other_tasks_vs_oracle(name):
+    """BASELINE configs 4 / 5 at full width: face restoration (8 latent channels, 512x512 LQ through the three-stage
+    feature extractor) and inpainting (LQ + mask at 256x256, two-stage extractor), batch 2 with distinct timesteps,
+    against the CPU oracle on fresh seeded inputs."""
+    from oracle import unet_oracle as uo
+    ucfg, _, m = _model(name, seed=5)
+    sd = random_state_dict(ucfg, 5)
+    g = torch.Generator().manual_seed(55)
+    x = torch.randn(2, ucfg.out_channels, 64, 64, generator=g)
+    lq = torch.rand(2, 3, ucfg.lq_size, ucfg.lq_size, generator=g) * 2 - 1
+    mask = (torch.rand(2, 1, ucfg.lq_size, ucfg.lq_size, generator=g) > 0.5).float() * 2 - 1 if ucfg.cond_mask else None
+    t = torch.tensor([0, 3])
+    ref = uo.unet_forward(sd, ucfg, x, t, lq=lq, mask=mask)
+    out = m(x.cuda(), t.cuda(), lq=lq.cuda(), mask=None if mask is None else mask.cuda())
+    assert not torch.isnan(out).any()
+    mx, mn = _report(f"forward {name} full size", out, ref)
+    assert mx <= FWD_MAX and mn <= FWD_MEAN
+
+
 def test_forward_rectangular_latent():
     """Non-square latent (chopped tiles / padded inputs): H=64, W=128."""
     from oracle import unet_oracle as uo
@@ -163,6 +183,28 @@ def test_loop_realsr_15_vs_reference_golden(golden_dir):
         mx, mn = _report(f"loop realsr sample step {k}", rec[k]["sample"], torch.from_numpy(g[f"sample/{k}"]))
         assert mx <= LOOP_MAX and mn <= LOOP_MEAN
     assert torch.equal(rec[-1]["sample"], final)
+
+
+def test_loop_faceir_4_steps_vs_oracle():
+    """The native 4-step schedule of the face-restoration task (8 latent channels, feature extractor hoisted out of the
+    loop) against the CPU oracle loop on the same z_y, noises and 512x512 LQ."""
+    from oracle import diffusion_oracle as do
+    from oracle import unet_oracle as uo
+    from resshift_b200.models.script_util import create_gaussian_diffusion
+    ucfg, dcfg, m = _model("faceir", seed=6)
+    sd = random_state_dict(ucfg, 6)
+    diff = create_gaussian_diffusion(**dcfg.to_kwargs())
+    g = torch.Generator().manual_seed(66)
+    zy = torch.randn(2, 8, 64, 64, generator=g) * 0.5
+    lq = torch.rand(2, 3, 512, 512, generator=g) * 2 - 1
+    noises = torch.stack([torch.randn(2, 8, 64, 64, generator=g) for _ in range(dcfg.steps + 1)])
+    tabs = do.schedule_tables(do.eta_schedule(dcfg.steps, dcfg.min_noise_level, dcfg.etas_end, dcfg.kappa,
+                                              dcfg.schedule_kwargs["power"]), dcfg.kappa)
+    ref = do.p_sample_loop(lambda x, t: uo.unet_forward(sd, ucfg, x, t, lq=lq), zy, list(noises), tabs, dcfg.kappa)
+    final = diff.sample_latent(zy.cuda(), m, {"lq": lq.cuda()}, noises=noises.cuda(), use_graph=True)
+    assert not torch.isnan(final).any()
+    mx, mn = _report("loop faceir T4", final, ref)
+    assert mx <= LOOP_MAX and mn <= LOOP_MEAN
 
 
 def test_batch_independence_at_bench_size():
