@@ -148,8 +148,8 @@ int rs_op_window_attention(const void* qkv, int N, int H, int W, int heads, int 
 int rs_op_mlp(const void* x, int N, int H, int W, int E, int Hd, const void* w1_packed, const float* b1,
               const void* w2_packed, const float* b2, const void* residual, void* out, void* dbg_timeline_or_null,
               void* stream);
-/* host-only: tile configuration the conv launcher picks: out[8] = BN, msub, stages, CTAs/SM, estimated cycles,
-   CTAs per tile group (1 or 2), split-K factor, persistent kernel (0 / 1) */
+/* host-only: tile configuration the conv launcher picks: out[9] = BN, msub, stages, CTAs/SM, estimated cycles,
+   CTAs per tile group (1 or 2), split-K factor, persistent kernel (0 / 1), cluster split-K (0 / 1) */
 int rs_debug_tile_config(int m_tiles, int cout, int num_kblocks, int32_t* out);
 /* nearest x2 (reference models/unet.py:71-81) */
 int rs_op_upsample2x(const void* x, int N, int H, int W, int C, void* y, void* stream);

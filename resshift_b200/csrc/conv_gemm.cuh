@@ -54,6 +54,8 @@ struct ConvParams {
   int splitk;            // > 1: the K loop is cut into `splitk` ranges, one CTA (or pair) each; the epilogue then only
                          //      stores fp32 partial accumulators to `partial` and splitk_reduce_kernel finishes the layer
   float* partial;        // [splitk][Nimg*Hout*Wout pixels][Cout] fp32
+  int splitk_cluster;    // 1 (pair mode only): the S K-ranges of a tile are ONE cluster of 2*S CTAs; partial tiles stay in
+                         //    shared memory and are summed through distributed shared memory (no scratch, no second kernel)
   int msub;              // 128-pixel sub-tiles per CTA (1 or 2): two sub-tiles share every weight tile (fewer operand bytes per MMA)
   // epilogue
   const float* bias;                 // [Cout] fp32 or nullptr
@@ -112,7 +114,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
   }
 
   // tile coordinates: CTA -> (channel tile, msub consecutive 128-pixel tiles)
-  const uint32_t rank = kCG == 2 ? cluster_ctarank() : 0;    // leader = rank 0
+  // pair mode: the cluster is one CTA pair — or, with splitk_cluster, the S pairs (K ranges) of one tile: cluster rank =
+  // 2 * split + (rank inside the pair); the pair's leader is the even rank
+  const uint32_t crank = kCG == 2 ? cluster_ctarank() : 0;
+  const uint32_t rank = crank & 1;                            // leader = rank 0
+  const uint32_t lead = crank & ~1u;                          // cluster rank of this pair's leader
+  const uint16_t pair_mask = (uint16_t)(3u << lead);          // multicast mask of this pair
   int unit = kCG == 2 ? (blockIdx.x >> 1) : blockIdx.x;       // work unit: a CTA, or a CTA pair
   const int split = unit % p.splitk;                          // which K range (fastest index: splits of a tile run together)
   unit /= p.splitk;
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
       const int kcol = kc * kConvBK, wcol = tap * p.w_tap_stride + kc * kConvBK;
       if constexpr (kCG == 2) {
         // both CTAs' loads complete on the LEADER's full barrier; only the leader arms it (with the bytes of both)
-        const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+        const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), lead);
         if (el) {
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_4d_cg2(sa, ma, lead_bar, kcol, w0s[0] + dw, h0s[0] + dh, n0s[0]);
@@ -217,8 +224,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
           umma_f16_cg2(tmem_base, adesc, bdesc, idesc, acc0);
 #pragma unroll
           for (int k = 1; k < kConvBK / 16; ++k) umma_f16_cg2(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
-          umma_commit_cg2(&empty_bar[stage], 3);                    // frees the stage in BOTH CTAs
-          if (kb == num_kb - 1) umma_commit_cg2(tmem_full_bar, 3);  // accumulators of both CTAs complete
+          umma_commit_cg2(&empty_bar[stage], pair_mask);                    // frees the stage in BOTH CTAs
+          if (kb == num_kb - 1) umma_commit_cg2(tmem_full_bar, pair_mask);  // accumulators of both CTAs complete
         }
       } else {
         if (el) {
@@ -259,7 +266,20 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
     tc_fence_after();
     if (dbg && etid == 0) dbg[4] = global_timer_ns();
 
-    if (p.splitk > 1) {
+    if (p.splitk > 1 && p.splitk_cluster) {
+      // ---------- cluster split-K, step 1: this K range's fp32 partial tile -> own shared memory ----------
+      // (the operand ring is free: every MMA has retired; row pitch BN*4 + 16 B spreads the rows over the banks)
+      const int pitch = p.BN * 4 + 16;
+      const uint32_t drow = smem_u32(smem) + (uint32_t)(r * pitch);
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int c = cpar * 16; c < p.BN; c += 32) {
+        uint32_t v[16];
+        tmem_ld16(trow + c, v);
+        tmem_ld_wait16(v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_shared_v4(drow + (uint32_t)(c * 4 + j * 16), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    } else if (p.splitk > 1) {
       // ---------- split-K: raw fp32 partial sums, finished by splitk_reduce_kernel ----------
       int tw, th, w0, h0, n0;
       tile_origin(0, tw, th, w0, h0, n0);
@@ -493,6 +513,108 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
               p.out_f32_nchw[(((long long)n * p.Cout + (col + j)) * p.Hout + h) * p.Wout + w] = f[j];
           if (orow)
             for (int j = 0; j < 16 && col + j < p.Cout; ++j) orow[col + j] = __float2half_rn(f[j]);
+        }
+      }
+    }
+  }
+
+  if constexpr (kCG == 2) {
+    if (p.splitk > 1 && p.splitk_cluster) {
+      // ---------- cluster split-K, step 2: sum the S partial tiles through distributed shared memory ----------
+      // K range `split` finishes columns [split * BN/S, (split + 1) * BN/S) of the tile for its CTA's 128 pixels:
+      // fixed summation order (range 0, 1, ...), then the usual epilogue work (bias / activation / residual / fp16
+      // store / GroupNorm partials of the stored values).  Deterministic, no global scratch, no second kernel.
+      cluster_sync_all();                                   // every K range's partial tile is in its CTA's shared memory
+      if (warp < kConvEpiWarps) {
+        const int etid = threadIdx.x;
+        const int S = p.splitk, cw = p.BN / S, upr = cw >> 3;
+        const int pitch = p.BN * 4 + 16;
+        const int cbase = split * cw;
+        const int col0 = n_tile * p.BN;
+        __half* s_out = reinterpret_cast<__half*>(smem + (size_t)kConvBM * pitch);        // [128][cw] stored values
+        float* s_col = reinterpret_cast<float*>(s_out + (size_t)kConvBM * cw);            // [2 halves][cw][2]
+        int tw, th, w0, h0, n0;
+        tile_origin(0, tw, th, w0, h0, n0);
+        const uint32_t dump0 = smem_u32(smem);
+        for (int u = etid; u < kConvBM * upr; u += 32 * kConvEpiWarps) {
+          const int rr = u / upr, cu = u - rr * upr;
+          const int ct = cbase + cu * 8;                    // column inside the BN tile
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+          for (int sp = 0; sp < S; ++sp) {
+            const uint32_t a = mapa_u32(dump0 + (uint32_t)(rr * pitch + ct * 4), (uint32_t)(sp * 2) + rank);
+            const float4 x0 = ld_shared_cluster_f4(a), x1 = ld_shared_cluster_f4(a + 16);
+            acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
+            acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+          }
+          const int lw = rr % p.bw, lh = (rr / p.bw) % p.bh, ln = rr / (p.bw * p.bh);
+          const int w = w0 + lw, h = h0 + lh, n = n0 + ln;
+          const int col = col0 + ct;
+          const bool ok = (w < p.Wout) && (h < p.Hout) && (n < p.Nimg) && (col < p.Cout);   // Cout % 8 == 0
+          uint4 o = make_uint4(0, 0, 0, 0);
+          if (ok) {
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] += __ldg(p.bias + col + j);
+            }
+            if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = gelu_erf_f(acc[j]);
+            } else if (p.act == ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = silu_f(acc[j]);
+            }
+            if (p.residual) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + n * p.res_sN + h * p.res_sH + w * p.res_sW + col);
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(rh[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+            }
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+            *reinterpret_cast<uint4*>(p.out + n * p.out_sN + h * p.out_sH + w * p.out_sW + col) = o;
+          }
+          *reinterpret_cast<uint4*>(s_out + (size_t)rr * cw + cu * 8) = o;                  // zeros outside the tensor
+        }
+        if (p.gn_part[0] != nullptr) {
+          named_bar_sync(1, 32 * kConvEpiWarps);
+          // column sums of the stored values over the two 64-row halves, rows in order
+          for (int t = etid; t < 2 * cw; t += 32 * kConvEpiWarps) {
+            const int half = t / cw, c = t - half * cw;
+            float sv = 0.f, qv = 0.f;
+            for (int rr = half * 64; rr < half * 64 + 64; ++rr) {
+              const float v = __half2float(s_out[(size_t)rr * cw + c]);
+              sv += v; qv += v * v;
+            }
+            s_col[(half * cw + c) * 2] = sv; s_col[(half * cw + c) * 2 + 1] = qv;
+          }
+          named_bar_sync(1, 32 * kConvEpiWarps);
+          if (n0 < p.Nimg) {
+            const int slot = th * p.tiles_w + tw;
+            for (int c = etid; c < cw; c += 32 * kConvEpiWarps) {
+              const int col = col0 + cbase + c;
+              if (col >= p.Cout) continue;
+              const float sl = s_col[c * 2], ql = s_col[c * 2 + 1], sh = s_col[(cw + c) * 2], qh = s_col[(cw + c) * 2 + 1];
+#pragma unroll
+              for (int dI = 0; dI < 2; ++dI) {
+                float* part = p.gn_part[dI];
+                if (!part) continue;
+                const size_t ch = (size_t)p.gn_coff[dI] + col;
+                float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[dI] + ch) * 2;
+                if (p.bn == 1) {
+                  dst[0] = sl + sh; dst[1] = ql + qh;
+                } else {   // two images per tile: rows 0..63 -> n0, rows 64..127 -> n0 + 1
+                  dst[0] = sl; dst[1] = ql;
+                  if (n0 + 1 < p.Nimg) {
+                    float* dst1 = part + (((size_t)(n0 + 1) * p.gn_slots + slot) * p.gn_cstride[dI] + ch) * 2;
+                    dst1[0] = sh; dst1[1] = qh;
+                  }
+                }
+              }
+            }
+          }
         }
       }
     }

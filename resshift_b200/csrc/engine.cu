@@ -352,8 +352,8 @@ struct Builder {
     op.to_f32 = out_f32;
     if (out && !out_f32 && env_int("RS_CONV_SPLITK", 0) != 1) {       // split-K for layers with too few tiles
       const TileConfig tc = conv_preview_config(in.N, in.H, in.W, in.C, cout, ksize, stride, true);
-      if (tc.splitk > 1) {
-        op.conv.allow_split = true;
+      if (tc.splitk > 1) op.conv.allow_split = true;
+      if (tc.splitk > 1 && !tc.cluster_split) {       // (cluster split-K reduces through shared memory: no scratch)
         const size_t bytes = (size_t)tc.splitk * in.N * (in.H / stride) * (in.W / stride) * cout * sizeof(float);
         op.split_tens = P.new_tensor(bytes);
         Tensor& tz = P.tensors[op.split_tens];
@@ -707,7 +707,7 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       if (d.in.C < d.ipad && d.in.ld >= d.ipad && d.in.tens == P.xin.tens) d.in.C = d.ipad;
       if (d.in.C < d.ipad && P.fe_in.tens >= 0 && d.in.tens == P.fe_in.tens) d.in.C = d.ipad;
       int rc = conv_finalize(d); if (rc) return rc;
-      P.launches += d.prm.splitk > 1 ? 2 : 1;
+      P.launches += (d.prm.splitk > 1 && !d.prm.splitk_cluster) ? 2 : 1;
     } else if (op.kind == OP_GN) {
       resolve(P, op.gn.in); resolve(P, op.gn.out);
       op.gn.gamma = E.at<float>(op.g_name + ".weight"); op.gn.beta = E.at<float>(op.g_name + ".bias");

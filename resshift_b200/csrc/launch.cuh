@@ -156,14 +156,15 @@ struct ConvDesc {
   int grid = 0; size_t smem = 0;
 };
 
-struct TileConfig { int BN = 0, msub = 1, stages = 2, occ = 1, cg = 1, splitk = 1, persist = 0; double est_cycles = 1e30; };
+struct TileConfig { int BN = 0, msub = 1, stages = 2, occ = 1, cg = 1, splitk = 1, persist = 0, cluster_split = 0; double est_cycles = 1e30; };
 
 // Cost model calibrated on B200 timelines (profiles/r1_s5_*, r1_s6_*).  Per 64-channel k-block and 128-pixel tile the
 // tensor pipe needs 2*BN cycles; every operand byte crosses shared memory twice (TMA write + UMMA read, 128 B/clk
 // per SM), which is what actually bounds a single-CTA tile (A 16 KB + B BN*128 B);  a CTA pair (cg = 2,
 // tcgen05 cta_group::2) stages only half of B per SM.  Shallow rings are additionally latency-bound (~3000 cycles
 // per load).  The epilogue (~18 cycles per column + set-up) hides under a co-resident CTA; whole waves are counted.
-inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn, bool allow_split = false, bool allow_persist = false) {
+inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn, bool allow_split = false, bool allow_persist = false,
+                                   bool allow_cluster_split = false) {
   const int f_msub = env_int("RS_CONV_MSUB", 0), f_occ = env_int("RS_CONV_OCC", 0), f_stages = env_int("RS_CONV_STAGES", 0);
   const int f_cg = env_int("RS_CONV_CG", 0);
   TileConfig best, bestp;      // best one-tile-per-CTA configuration (ranking model below), best persistent one
@@ -219,23 +220,34 @@ inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn
           // split-K: S CTAs (pairs) share one output tile's K loop; costs an fp32 round trip + a small reduce kernel
           const int f_split = env_int("RS_CONV_SPLITK", 0);
           const int kSplits[6] = {1, 2, 3, 4, 6, 8};
+          // split-K flavours: 0 = none / global (fp32 partials in HBM scratch + splitk_reduce_kernel), 1 = cluster (the S
+          // pairs of a tile are one cluster of 2S CTAs and reduce through distributed shared memory: pair mode)
+          const char* f_mode = std::getenv("RS_CONV_SPLITK_MODE");
+          for (int mode = 0; mode < 2; ++mode)
           for (int si = 0; si < 6; ++si) {
             const int S = kSplits[si];
-            if (S > 1 && (!allow_split || ms != 1 || num_kb / S < 6)) continue;
-            if (f_split && allow_split && ms == 1 && num_kb / f_split >= 6 && S != f_split) continue;
+            // (S = 2 only: clusters of 8 CTAs with ~200 KB of shared memory each schedule poorly — 30 us vs 21 us for the
+            //  8x8 640->640 layer, profiles/r1_s35_cluster_split_sweep.log)
+            if (mode == 1 && (S != 2 || !allow_cluster_split || cg != 2 || occ != 1 || (cand / S) % 8 != 0)) continue;
+            if (mode == 1 && f_mode && std::strcmp(f_mode, "global") == 0) continue;
+            if (mode == 0 && S > 1 && f_mode && std::strcmp(f_mode, "cluster") == 0) continue;
+            if (mode == 1 && (size_t)kConvBM * (cand * 4 + 16) + (size_t)kConvBM * (cand / S) * 2 + (size_t)4 * (cand / S) * 4 > (size_t)st * sbytes) continue;
+            if (S > 1 && ((mode == 0 && !allow_split) || ms != 1 || num_kb / S < 6)) continue;
+            if (f_split && (allow_split || allow_cluster_split) && ms == 1 && num_kb / f_split >= 6 && S != f_split) continue;
             const double waves = std::ceil((double)units * S / slots);
             const double kbs = std::ceil((double)num_kb / S);
             const double round = kbs * kb_cycles + (occ == 2 ? 0.5 * epi : epi);
-            // fp32 partials: written once by the conv epilogue and read once by the reduce kernel (~2 KB/clk chip-wide
-            // each way in practice), plus a second kernel launch / drain (~10 us of fixed cost for the pair)
+            // global: fp32 partials written once by the conv epilogue and read once by the reduce kernel (~2 KB/clk
+            // chip-wide each way in practice), plus a second kernel launch / drain (~10 us of fixed cost for the pair);
+            // cluster: a cluster barrier and one pass over the tile through distributed shared memory
             const double part_bytes = 4.0 * m_tiles * 128.0 * cout16 * S;
-            const double total = waves * round + (S > 1 ? 19000.0 + 2.0 * part_bytes / 2048.0 : 0.0);
+            const double total = waves * round + (S == 1 ? 0.0 : mode == 1 ? 6000.0 : 19000.0 + 2.0 * part_bytes / 2048.0);
             if (total < best.est_cycles) {
               best.est_cycles = total; best.BN = cand; best.msub = ms; best.stages = std::min(st, (int)std::max(2.0, kbs));
-              best.occ = occ; best.cg = cg; best.splitk = S; best.persist = 0;
+              best.occ = occ; best.cg = cg; best.splitk = S; best.persist = 0; best.cluster_split = (S > 1 && mode == 1) ? 1 : 0;
               // what a wave really costs (timelines r1_s25): co-resident CTAs run in lockstep, so set-up, the first
               // operand round trip and the whole epilogue are exposed once per wave
-              best_real = waves * (kbs * kb_cycles + epi + 5000.0) + (S > 1 ? 19000.0 + 2.0 * part_bytes / 2048.0 : 0.0);
+              best_real = waves * (kbs * kb_cycles + epi + 5000.0) + (S == 1 ? 0.0 : mode == 1 ? 6000.0 : 19000.0 + 2.0 * part_bytes / 2048.0);
             }
           }
         }
@@ -258,7 +270,8 @@ inline TileConfig conv_preview_config(int N, int Hin, int Win, int Cin, int Cout
   const int m_tiles = (Wout / bw) * (Hout / bh) * ((N + bn - 1) / bn);
   const bool contiguous = (bw == Wout) || (bh == 1);
   const int num_kb = ksize * ksize * ((Cin + kConvBK - 1) / kConvBK);
-  return pick_tile_config(m_tiles, (Cout + 15) / 16 * 16, num_kb, env_int("RS_CONV_BN", 0), allow_split && contiguous && bn <= 2);
+  const bool sp = allow_split && contiguous && bn <= 2;
+  return pick_tile_config(m_tiles, (Cout + 15) / 16 * 16, num_kb, env_int("RS_CONV_BN", 0), sp, false, sp && Cout % 8 == 0);
 }
 
 inline int conv_finalize(ConvDesc& d) {
@@ -291,11 +304,12 @@ inline int conv_finalize(ConvDesc& d) {
   const int want_persist = env_int("RS_CONV_PERSIST", -1);           // 0 / 1 disables / forces the persistent kernel
   const bool persist_ok = d.has_out && !d.out_f32 && want_persist != 0 && !env_is("RS_CONV_EPI", "direct") &&
                           !env_is("RS_CONV_IMPL", "simt") && env_int("RS_CONV_MSUB", 0) != 2;
+  const bool can_cluster_split = d.allow_split && contiguous_tiles && p.bn <= 2 && d.has_out && !d.out_f32 && d.Cout % 8 == 0;
   const TileConfig tc = pick_tile_config(m_tiles, cout16, num_kb, d.bn_override ? d.bn_override : env_int("RS_CONV_BN", 0), can_split,
-                                         persist_ok && want_persist != 1);
+                                         persist_ok && want_persist != 1, can_cluster_split);
   const int BN = tc.BN, msub = tc.msub, stages = tc.stages, cg = tc.cg;
   p.cg = cg;
-  p.splitk = tc.splitk; p.partial = d.partial;
+  p.splitk = tc.splitk; p.partial = d.partial; p.splitk_cluster = tc.cluster_split;
   RS_CHECK(BN >= 16 && BN <= 256 && BN % 16 == 0, "no valid tile configuration");
   p.BN = BN; p.n_tiles = (cout16 + BN - 1) / BN;
   p.msub = msub;
@@ -378,7 +392,14 @@ inline int conv_finalize(ConvDesc& d) {
   if (p.gn_part[0] == nullptr && p.gn_part[1] != nullptr) {
     p.gn_part[0] = p.gn_part[1]; p.gn_cstride[0] = p.gn_cstride[1]; p.gn_coff[0] = p.gn_coff[1]; p.gn_part[1] = nullptr;
   }
-  if (p.splitk > 1) {
+  if (p.splitk > 1 && p.splitk_cluster) {
+    // cluster split-K: the conv kernel finishes the layer itself (DSMEM reduce + direct epilogue), statistics included
+    for (int i = 0; i < 2; ++i) { p.gn_part[i] = d.gn_part[i]; }
+    if (p.gn_part[0] == nullptr && p.gn_part[1] != nullptr) {
+      p.gn_part[0] = p.gn_part[1]; p.gn_cstride[0] = p.gn_cstride[1]; p.gn_coff[0] = p.gn_coff[1]; p.gn_part[1] = nullptr;
+    }
+    RS_CHECK(cg == 2 && d.Cout % 8 == 0 && (BN / p.splitk) % 8 == 0, "cluster split-K configuration");
+  } else if (p.splitk > 1) {
     // the conv kernel only produces fp32 partial sums; bias / activation / residual / fp16 store / GroupNorm partials
     // happen in the reduce kernel, one CTA per (128-pixel slot, image)
     SplitKReduceParams& r = d.red;
@@ -451,10 +472,11 @@ inline int conv_launch(const ConvDesc& d, cudaStream_t st) {
     else if (d.prm.persist)
       (void)launch_kc(conv_gemm_persist_sm100_kernel<1>, dim3(d.grid), dim3(kConvThreads), (size_t)(d.smem), st, 1, d.prm);
     else if (d.prm.cg == 2)
-      (void)launch_kc(conv_gemm_sm100_kernel<2>, dim3(d.grid), dim3(kConvThreads), (size_t)(d.smem), st, 2, d.prm);
+      (void)launch_kc(conv_gemm_sm100_kernel<2>, dim3(d.grid), dim3(kConvThreads), (size_t)(d.smem), st,
+                      d.prm.splitk_cluster ? 2 * d.prm.splitk : 2, d.prm);
     else
       (void)launch_kc(conv_gemm_sm100_kernel<1>, dim3(d.grid), dim3(kConvThreads), (size_t)(d.smem), st, 1, d.prm);
-    if (d.prm.splitk > 1)
+    if (d.prm.splitk > 1 && !d.prm.splitk_cluster)
       (void)launch_k(splitk_reduce_kernel, dim3(d.red_grid_x, d.prm.Nimg, d.red_grid_z), dim3(256), d.red_smem, st, d.red);
   }
   RS_CUDA_OK(cudaGetLastError());

@@ -1,7 +1,6 @@
 #!/bin/bash
-# GPU session 34: full GPU suite (incl. full-size faceir / inpaint parity), smoke(), bench lines (own arm + reference arm)
+# GPU session 36: cluster split-K restricted to S = 2
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
-timeout 900 python bench.py > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err; cat gpurun_out/bench_default.log | cut -c1-300
-timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.log | cut -c1-400
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_unet.py -x -q 2>&1 | tail -4
+timeout 300 python scripts/profile_ops.py > gpurun_out/per_op.log 2>&1; head -14 gpurun_out/per_op.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b16.log 2> gpurun_out/bench_b16.err; cat gpurun_out/bench_b16.log | cut -c1-420

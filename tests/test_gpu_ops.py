@@ -182,12 +182,17 @@ def test_conv2d_persistent_matches_one_tile_per_cta(case, cg):
     assert (G.nchw32(outs[1]) - ref).abs().max().item() <= _tol(ref)
 
 
+@pytest.mark.parametrize("mode", ["global", "cluster"])
 @pytest.mark.parametrize("force", [0, 2, 4])
 @pytest.mark.parametrize("case", [(16, 8, 8, 640, 640, 3), (3, 16, 16, 320, 320, 3), (5, 8, 8, 192, 192, 1), (2, 16, 16, 960, 320, 3)])
-def test_conv2d_split_k(case, force):
-    """Layers with few output tiles split their K loop over several CTAs; fp32 partial sums are combined in a fixed
-    order by the reduce kernel, which also applies bias / residual and emits the GroupNorm partial statistics."""
+def test_conv2d_split_k(case, force, mode):
+    """Layers with few output tiles split their K loop over several CTAs (pairs).  `global`: fp32 partial sums go to a
+    scratch buffer and the reduce kernel combines them in a fixed order, applies bias / residual and emits the GroupNorm
+    partial statistics.  `cluster`: the K ranges of a tile form one thread-block cluster, keep their partial tiles in
+    shared memory and finish the layer themselves through distributed shared memory (no scratch, no second kernel)."""
     import ctypes as C
+    if mode == "cluster" and force == 4:
+        pytest.skip("cluster split-K is limited to two K ranges (clusters of 4 CTAs)")
     N, H, W, Ci, Co, k = case
     g = torch.Generator(device="cuda").manual_seed(sum(case))
     x = G.nhwc16(torch.randn(N, Ci, H, W, device="cuda", generator=g))
@@ -198,6 +203,7 @@ def test_conv2d_split_k(case, force):
     scratch = torch.empty(8 * N * H * W * Co, dtype=torch.float32, device="cuda")
     if force:
         os.environ["RS_CONV_SPLITK"] = str(force)
+    os.environ["RS_CONV_SPLITK_MODE"] = mode
     try:
         outs, parts, used = [], [], []
         for rep in range(2):
@@ -211,7 +217,8 @@ def test_conv2d_split_k(case, force):
             outs.append(out); parts.append(part.clone()); used.append(S.value)
     finally:
         os.environ.pop("RS_CONV_SPLITK", None)
-    print(f"[split-k] case {case} forced {force}: S = {used[0]}")
+        os.environ.pop("RS_CONV_SPLITK_MODE", None)
+    print(f"[split-k] case {case} forced {force} mode {mode}: S = {used[0]}")
     assert torch.equal(outs[0], outs[1]) and torch.equal(parts[0][~torch.isnan(parts[0])], parts[1][~torch.isnan(parts[1])])
     ref = G.ref_conv(x, w, b, residual=res)
     st = G.err_stats(G.nchw32(outs[0]), ref)
