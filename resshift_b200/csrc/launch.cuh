@@ -597,7 +597,19 @@ inline int mlp_finalize(MlpDesc& d) {
   p.ring2 = (int)std::min<size_t>(2 * kHT, (budget - (size_t)kx * kW1) / slot2);
   p.ring1 = (int)std::min<size_t>(12, (budget - (size_t)p.ring2 * slot2) / kW1);
   p.has_res = d.has_res ? 1 : 0;
-  d.grid = p.tiles_w * p.tiles_h * tiles_n;      // even (mlp_supported): CTA pairs
+  const int tiles = p.tiles_w * p.tiles_h * tiles_n;      // even (mlp_supported): CTA pairs
+  // few-tile layers (8x8 / 16x16 levels): split the hidden dimension over two pairs of one cluster; partial outputs
+  // meet in distributed shared memory (RS_MLP_HSPLIT = 1 disables, = 2 forces)
+  {
+    const int want = env_int("RS_MLP_HSPLIT", 0);
+    const bool can = (d.Hd / kMlpHc) >= 2 && (d.E / 2) % 8 == 0 &&
+                     (size_t)kConvBM * (d.E * 4 + 16) + (size_t)kConvBM * (d.E / 2) * 2 + (size_t)2 * d.E * 4 <= (size_t)200 * 1024;
+    p.hsplit = (can && want != 1 && (want == 2 || tiles <= 64)) ? 2 : 1;
+  }
+  d.grid = tiles * p.hsplit;
+  p.out_ptr = d.out.ptr; p.out_sN = d.out.sN(); p.out_sH = d.out.sH(); p.out_sW = d.out.sW();
+  p.res_ptr = d.has_res ? d.res.ptr : nullptr;
+  if (d.has_res) { p.res_sN = d.res.sN(); p.res_sH = d.res.sH(); p.res_sW = d.res.sW(); }
   d.smem = fixed + (size_t)p.ring1 * kW1 + (size_t)p.ring2 * slot2;
   RS_CHECK(d.smem <= 227 * 1024, "fused MLP: shared memory budget exceeded");
   int rc = encode_act_map(&p.tmX, d.in.ptr, d.E, W, H, N, d.in.sW(), d.in.sH(), d.in.sN(), p.bw, p.bh, p.bn, 64);
@@ -624,7 +636,7 @@ inline int mlp_finalize(MlpDesc& d) {
 }
 
 inline int mlp_launch(const MlpDesc& d, cudaStream_t st) {
-  (void)launch_kc(mlp_fused_sm100_kernel, dim3(d.grid), dim3(kMlpThreads), d.smem, st, 2, d.prm);
+  (void)launch_kc(mlp_fused_sm100_kernel, dim3(d.grid), dim3(kMlpThreads), d.smem, st, 2 * d.prm.hsplit, d.prm);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -40,6 +40,11 @@ struct MlpParams {
   int bw, bh, bn, tiles_w, tiles_h;
   int Wout, Hout, Nimg;
   int has_res;
+  const __half* res_ptr; long long res_sN, res_sH, res_sW;   // raw NHWC views for the hsplit epilogue
+  __half* out_ptr; long long out_sN, out_sH, out_sW;
+  int hsplit;                        // 1, or 2: the hidden dimension is split over two CTA pairs of one cluster (few-tile
+                                     // layers); each pair walks half of the chunks and the partial outputs are summed
+                                     // through distributed shared memory, each pair finishing half of the E columns
   float* gn_part[2]; int gn_cstride[2]; int gn_coff[2]; int gn_slots;
   long long* dbg;                    // optional: CTA 0 writes a clock64 timeline [64 chunks][8] (profiling aid)
   // optional fused input GroupNorm (the Swin block's norm2, models/swin_transformer.py:279): X is then the UN-normalised
@@ -59,7 +64,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kx = p.E >> 6;                         // k-blocks of the first GEMM
-  const int chunks = p.Hd / kMlpHc;
+  const int chunks_total = p.Hd / kMlpHc;
   constexpr int kTile = kConvBM * kConvBK * 2;     // 16 KB: 128 rows x 64 fp16
   constexpr int kW1 = (kMlpHc / 2) * kConvBK * 2;  // this CTA's half of an fc1 weight tile: kMlpHc/2 rows x 64 fp16
   constexpr int kHT = kMlpHc / kConvBK;            // 64-column tiles per hidden chunk (= k-blocks of the second GEMM)
@@ -92,8 +97,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
   // CTA pair (cluster of 2, tcgen05 cta_group::2): a 256-pixel tile, 128 pixels per CTA.  Each CTA stages only HALF of
   // every weight tile, so the same shared memory holds two hidden chunks of both weight streams in flight (one chunk
   // deep the loop is a chain of exposed load latencies: profiles/r1_s18_*), and the L2 -> SM weight traffic halves.
-  const uint32_t rank = cluster_ctarank();         // leader = rank 0: arms the operand barriers, issues every MMA
-  int mt = (blockIdx.x >> 1) * 2 + (int)rank;
+  // cluster rank = 2 * (hidden-dimension split) + (rank inside the pair); the pair's leader is the even rank
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;                 // leader = rank 0: arms the operand barriers, issues every MMA
+  const uint32_t lead = crank & ~1u;
+  const uint16_t pmask = (uint16_t)(3u << lead);   // multicast mask of this pair
+  const int hs = (int)(crank >> 1);
+  const int jc0 = hs * chunks_total / p.hsplit;                    // this pair's chunk range [jc0, jc0 + chunks)
+  const int chunks = (hs + 1) * chunks_total / p.hsplit - jc0;
+  int mt = (int)(blockIdx.x / (2 * p.hsplit)) * 2 + (int)rank;
   const int tw = mt % p.tiles_w; mt /= p.tiles_w;
   const int th = mt % p.tiles_h; mt /= p.tiles_h;
   const int w0 = tw * p.bw, h0 = th * p.bh, n0 = mt * p.bn;
@@ -126,7 +138,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
     // ===================== TMA producer 1: X once, then the fc1 weight stream =====================
     // (the two weight streams have a warp each: a lane blocked in mbarrier.try_wait stalls its whole warp)
     const bool el = elect_one();
-    const uint32_t lead_x = mapa_u32(smem_u32(x_full), 0);
+    const uint32_t lead_x = mapa_u32(smem_u32(x_full), lead);
     if (el) {
       if (p.gn_in_part) {
         // fused input GroupNorm: each CTA's GELU warps wait for their OWN tile, normalise it, then signal the leader
@@ -143,10 +155,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
       for (int kb = 0; kb < kx; ++kb) {
         mbar_wait(&w1_empty[st1], ph1 ^ 1);
         // both CTAs' halves complete on the LEADER's barrier; only the leader arms it (with the bytes of both)
-        const uint32_t lead_bar = mapa_u32(smem_u32(&w1_full[st1]), 0);
+        const uint32_t lead_bar = mapa_u32(smem_u32(&w1_full[st1]), lead);
         if (el) {
           if (rank == 0) mbar_arrive_expect_tx(&w1_full[st1], (uint32_t)(2 * kW1));
-          tma_load_2d_cg2(sW1 + (size_t)st1 * kW1, &p.tmW1, lead_bar, kb * kConvBK, j * kMlpHc + row0);
+          tma_load_2d_cg2(sW1 + (size_t)st1 * kW1, &p.tmW1, lead_bar, kb * kConvBK, (jc0 + j) * kMlpHc + row0);
         }
         if (++st1 == p.ring1) { st1 = 0; ph1 ^= 1; }
       }
@@ -158,10 +170,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
     for (int j = 0; j < chunks; ++j)
       for (int t = 0; t < kHT; ++t) {
         mbar_wait(&w2_empty[st2], ph2 ^ 1);
-        const uint32_t lead_bar = mapa_u32(smem_u32(&w2_full[st2]), 0);
+        const uint32_t lead_bar = mapa_u32(smem_u32(&w2_full[st2]), lead);
         if (el) {
           if (rank == 0) mbar_arrive_expect_tx(&w2_full[st2], (uint32_t)(2 * slot2));
-          tma_load_2d_cg2(sW2 + (size_t)st2 * slot2, &p.tmW2, lead_bar, j * kMlpHc + t * kConvBK, row0);
+          tma_load_2d_cg2(sW2 + (size_t)st2 * slot2, &p.tmW2, lead_bar, (jc0 + j) * kMlpHc + t * kConvBK, row0);
         }
         if (++st2 == p.ring2) { st2 = 0; ph2 ^= 1; }
       }
@@ -190,8 +202,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
             umma_f16_cg2(d, adesc, bdesc, idesc1, kb != 0 ? 1u : 0u);
 #pragma unroll
             for (int k = 1; k < 4; ++k) umma_f16_cg2(d, adesc + 2 * k, bdesc + 2 * k, idesc1, 1u);
-            umma_commit_cg2(&w1_empty[st1], 3);                       // frees the slot in BOTH CTAs
-            if (kb == kx - 1) umma_commit_cg2(&acc1_full[b], 3);
+            umma_commit_cg2(&w1_empty[st1], pmask);                       // frees the slot in BOTH CTAs
+            if (kb == kx - 1) umma_commit_cg2(&acc1_full[b], pmask);
           }
           if (++st1 == p.ring1) { st1 = 0; ph1 ^= 1; }
         }
@@ -215,10 +227,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
             umma_f16_cg2(tm_acc2, adesc, bdesc, idesc2, (j | t) != 0 ? 1u : 0u);
 #pragma unroll
             for (int k = 1; k < 4; ++k) umma_f16_cg2(tm_acc2, adesc + 2 * k, bdesc + 2 * k, idesc2, 1u);
-            umma_commit_cg2(&w2_empty[st2], 3);
+            umma_commit_cg2(&w2_empty[st2], pmask);
             if (t == kHT - 1) {
-              umma_commit_cg2(&h_empty[b], 3);
-              if (j == chunks - 1) umma_commit_cg2(acc2_full, 3);
+              umma_commit_cg2(&h_empty[b], pmask);
+              if (j == chunks - 1) umma_commit_cg2(acc2_full, pmask);
             }
           }
           if (++st2 == p.ring2) { st2 = 0; ph2 ^= 1; }
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
       }
       fence_proxy_async_smem();                                     // the tensor core reads X through the async proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(x_ready), 0));
+      if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(x_ready), lead));
       named_bar_sync(1, 32 * kMlpEpiWarps);                         // s_sum (aliasing the bias area) is free again
     }
     for (int i = etid; i < p.Hd; i += 32 * kMlpEpiWarps) s_b1[i] = __ldg(p.bias1 + i);
@@ -318,8 +330,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
     named_bar_sync(1, 32 * kMlpEpiWarps);
     const int c16 = cpar * 16;
     const int u0 = c16 >> 3;                       // 16-byte unit of this warp's first 8 columns inside a 128-byte row
-    const uint32_t lead_acc1_empty = mapa_u32(smem_u32(acc1_empty), 0);
-    const uint32_t lead_h_full = mapa_u32(smem_u32(h_full), 0);
+    const uint32_t lead_acc1_empty = mapa_u32(smem_u32(acc1_empty), lead);
+    const uint32_t lead_h_full = mapa_u32(smem_u32(h_full), lead);
     for (int j = 0; j < chunks; ++j) {
       const int b = j & 1;
       mbar_wait(&acc1_full[b], (j >> 1) & 1);
@@ -334,7 +346,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
       for (int t = 0; t < kHT; ++t) tmem_ld_wait16(v[t]);
 #pragma unroll
       for (int t = 0; t < kHT; ++t) {
-        const float4* bp = reinterpret_cast<const float4*>(s_b1 + j * kMlpHc + t * kConvBK + c16);
+        const float4* bp = reinterpret_cast<const float4*>(s_b1 + (jc0 + j) * kMlpHc + t * kConvBK + c16);
         uint32_t q[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -361,6 +373,19 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
     mbar_wait(acc2_full, 0);
     tc_fence_after();
     if (dbg && etid == 0) dbg[63 * 8 + 0] = clock64() - t_start;
+    if (p.hsplit > 1) {
+      // hidden-dimension split, step 1: this pair's partial output tile (fp32) -> own shared memory (everything the
+      // MMAs read is dead now); the cluster-wide reduction follows after the role branches
+      const int pitch = p.E * 4 + 16;
+      const uint32_t drow = smem_u32(smem) + (uint32_t)(r * pitch);
+      for (int c = cpar * 16; c < p.E; c += 64) {
+        uint32_t v[16];
+        tmem_ld16(tm_acc2 + lane_base + c, v);
+        tmem_ld_wait16(v);
+#pragma unroll
+        for (int jv = 0; jv < 4; ++jv) st_shared_v4(drow + (uint32_t)(c * 4 + jv * 16), v[4 * jv], v[4 * jv + 1], v[4 * jv + 2], v[4 * jv + 3]);
+      }
+    } else {
     const int lw = r % p.bw, lh = (r / p.bw) % p.bh, ln = r / (p.bw * p.bh);
     const bool row_ok = (w0 + lw < p.Wout) && (h0 + lh < p.Hout) && (n0 + ln < p.Nimg);
     const int nblk = p.E >> 6;
@@ -480,7 +505,92 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
       }
     }
     if (etid == 0) tma_store_wait_read();
+    }
     if (dbg && etid == 0) dbg[63 * 8 + 1] = clock64() - t_start;
+  }
+
+  if (p.hsplit > 1) {
+    // ---- hidden-dimension split, step 2: sum the pairs' partial tiles through distributed shared memory ----
+    // pair `hs` finishes columns [hs * E / hsplit, (hs + 1) * E / hsplit) for its CTAs' 128 pixels each: fixed order
+    // (split 0, 1), + bias2, + residual, fp16 store, GroupNorm partials of the stored values.
+    cluster_sync_all();
+    if (warp < kMlpEpiWarps) {
+      const int etid = threadIdx.x;
+      const int S = p.hsplit, cw = p.E / S, upr = cw >> 3;
+      const int pitch = p.E * 4 + 16;
+      const int cbase = hs * cw;
+      __half* s_out = reinterpret_cast<__half*>(smem + (size_t)kConvBM * pitch);        // [128][cw] stored values
+      float* s_col = reinterpret_cast<float*>(s_out + (size_t)kConvBM * cw);            // [2 halves][cw][2]
+      const uint32_t dump0 = smem_u32(smem);
+      for (int u = etid; u < kConvBM * upr; u += 32 * kMlpEpiWarps) {
+        const int rr = u / upr, cu = u - rr * upr;
+        const int col = cbase + cu * 8;
+        float acc[8];
+#pragma unroll
+        for (int jv = 0; jv < 8; ++jv) acc[jv] = 0.f;
+        for (int sp = 0; sp < S; ++sp) {
+          const uint32_t a = mapa_u32(dump0 + (uint32_t)(rr * pitch + col * 4), (uint32_t)(sp * 2) + rank);
+          const float4 x0 = ld_shared_cluster_f4(a), x1 = ld_shared_cluster_f4(a + 16);
+          acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
+          acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+        }
+        const int lw = rr % p.bw, lh = (rr / p.bw) % p.bh, ln = rr / (p.bw * p.bh);
+        const int w = w0 + lw, h = h0 + lh, n = n0 + ln;
+        const bool ok = (w < p.Wout) && (h < p.Hout) && (n < p.Nimg);
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (ok) {
+#pragma unroll
+          for (int jv = 0; jv < 8; ++jv) acc[jv] += __ldg(p.bias2 + col + jv);
+          if (p.has_res) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(p.res_ptr + n * p.res_sN + h * p.res_sH + w * p.res_sW + col);
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int jv = 0; jv < 4; ++jv) { const float2 f = __half22float2(rh[jv]); acc[2 * jv] += f.x; acc[2 * jv + 1] += f.y; }
+          }
+          __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int jv = 0; jv < 4; ++jv) oh[jv] = __floats2half2_rn(acc[2 * jv], acc[2 * jv + 1]);
+          *reinterpret_cast<uint4*>(p.out_ptr + n * p.out_sN + h * p.out_sH + w * p.out_sW + col) = o;
+        }
+        *reinterpret_cast<uint4*>(s_out + (size_t)rr * cw + cu * 8) = o;                  // zeros outside the tensor
+      }
+      if (p.gn_part[0] != nullptr) {
+        named_bar_sync(1, 32 * kMlpEpiWarps);
+        for (int t = etid; t < 2 * cw; t += 32 * kMlpEpiWarps) {
+          const int half = t / cw, c = t - half * cw;
+          float sv = 0.f, qv = 0.f;
+          for (int rr = half * 64; rr < half * 64 + 64; ++rr) {
+            const float v = __half2float(s_out[(size_t)rr * cw + c]);
+            sv += v; qv += v * v;
+          }
+          s_col[(half * cw + c) * 2] = sv; s_col[(half * cw + c) * 2 + 1] = qv;
+        }
+        named_bar_sync(1, 32 * kMlpEpiWarps);
+        if (n0 < p.Nimg) {
+          const int slot = th * p.tiles_w + tw;
+          for (int c = etid; c < cw; c += 32 * kMlpEpiWarps) {
+            const int col = cbase + c;
+            const float sl = s_col[c * 2], ql = s_col[c * 2 + 1], sh = s_col[(cw + c) * 2], qh = s_col[(cw + c) * 2 + 1];
+#pragma unroll
+            for (int dI = 0; dI < 2; ++dI) {
+              float* part = p.gn_part[dI];
+              if (!part) continue;
+              const size_t ch = (size_t)p.gn_coff[dI] + col;
+              float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[dI] + ch) * 2;
+              if (p.bn == 1) {
+                dst[0] = sl + sh; dst[1] = ql + qh;
+              } else {
+                dst[0] = sl; dst[1] = ql;
+                if (n0 + 1 < p.Nimg) {
+                  float* dst1 = part + (((size_t)(n0 + 1) * p.gn_slots + slot) * p.gn_cstride[dI] + ch) * 2;
+                  dst1[0] = sh; dst1[1] = qh;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
   }
 
   tc_fence_before();

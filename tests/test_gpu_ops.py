@@ -229,10 +229,13 @@ def test_conv2d_split_k(case, force, mode):
     assert (pv[..., 0].sum(1) - of.sum(dim=(1, 2))).abs().max().item() <= 1e-3 * (1 + of.sum(dim=(1, 2)).abs().max().item())
 
 
+@pytest.mark.parametrize("hsplit", [1, 2])
 @pytest.mark.parametrize("case", [(2, 16, 16, 192, 768), (1, 64, 64, 64, 256), (3, 8, 8, 192, 768), (4, 32, 32, 192, 768)])
-def test_fused_mlp(case):
+def test_fused_mlp(case, hsplit, monkeypatch):
     """out = residual + fc2(GELU(fc1(x))) in one kernel (hidden activations stay on chip, rounded to fp16 like the
-    unfused path rounds its stored intermediate)."""
+    unfused path rounds its stored intermediate).  hsplit = 2: the hidden dimension is split over two CTA pairs of one
+    cluster and the partial outputs are summed through distributed shared memory (few-tile layers)."""
+    monkeypatch.setenv("RS_MLP_HSPLIT", str(hsplit))
     N, H, W, E, Hd = case
     g = torch.Generator(device="cuda").manual_seed(sum(case))
     x = G.nhwc16(torch.randn(N, E, H, W, device="cuda", generator=g))
