@@ -269,6 +269,8 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // the staged shared memory has been READ by every committed store (it may be reused / the CTA may exit); the global
 // writes themselves complete asynchronously, at the latest at kernel completion
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// same, but the most recent committed store may still be reading (double-buffered staging)
+__device__ __forceinline__ void tma_store_wait_read_keep1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }

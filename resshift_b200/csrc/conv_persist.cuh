@@ -24,10 +24,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
   const int b_rows = kCG == 2 ? p.BN / 2 : p.BN;             // weight rows staged by THIS CTA
   const int b_bytes = b_rows * kConvBK * 2;
   const int stage_bytes = a_bytes + b_bytes;
-  uint8_t* s_stage = smem + (size_t)p.stages * stage_bytes;                 // [BN/bc blocks][128 rows][bc] fp16 (swizzled)
-  float* wsum = reinterpret_cast<float*>(s_stage + (size_t)p.BN * kConvBM * 2);   // [4 quads][BN][2]
-  float* s_bias = wsum + (size_t)4 * p.BN * 2;                              // [BN]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + p.BN);
+  const size_t stage_sz = (size_t)p.BN * kConvBM * 2;
+  uint8_t* s_stage0 = smem + (size_t)p.stages * stage_bytes;                // 2 x [BN/bc blocks][128 rows][bc] fp16 (swizzled):
+                                                                            // tile i stages while tile i-1's TMA store drains
+  float* wsum = reinterpret_cast<float*>(s_stage0 + 2 * stage_sz);          // [4 quads][BN][2]
+  float* s_bias0 = wsum + (size_t)4 * p.BN * 2;                             // 2 x [BN]: this tile's / the next tile's bias
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias0 + 2 * p.BN);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* acc_full = empty_bar + p.stages;       // [2] per CTA (multicast commit in pair mode)
   uint64_t* acc_empty = acc_full + 2;              // [2] leader's: one arrival per epilogue warp (of both CTAs)
@@ -172,28 +174,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
     const bool want_stats = p.gn_part[0] != nullptr;
     const uint32_t lead_acc_empty = kCG == 2 ? mapa_u32(smem_u32(acc_empty), 0) : smem_u32(acc_empty);
     int i = 0;
-    int bias_tile = -1;
+    auto load_bias = [&](int u, float* dst) {
+      const int c0 = (u % p.n_tiles) * p.BN;
+      for (int c = etid; c < p.BN; c += 32 * kConvEpiWarps) dst[c] = (p.bias && c0 + c < p.Cout) ? __ldg(p.bias + c0 + c) : 0.f;
+    };
+    if (worker < p.num_units) load_bias(worker, s_bias0);          // visible after the first tile's opening barrier
     for (int u = worker; u < p.num_units; u += num_workers, ++i) {
       const int b = i & 1;
       int n_tile, tw, th, w0, h0, n0;
       unit_tile(u, n_tile, tw, th, w0, h0, n0);
       const int col0 = n_tile * p.BN;
       const bool row_ok = (w0 + lw < p.Wout) && (h0 + lh < p.Hout) && (n0 + ln < p.Nimg);
-      // the previous tile's TMA store has read the staging buffer; its GroupNorm partials have been written out
-      if (etid == 0 && i > 0) tma_store_wait_read();
+      uint8_t* s_stage = s_stage0 + (size_t)b * stage_sz;
+      const float* s_bias = s_bias0 + (size_t)b * p.BN;
+      // this staging buffer was last used by tile i-2: its TMA store has read it (tile i-1's may still be draining);
+      // the opening barrier also publishes this tile's bias (loaded during tile i-1) and frees wsum / the other bias slot
+      if (etid == 0 && i >= 2) tma_store_wait_read_keep1();
       named_bar_sync(1, 32 * kConvEpiWarps);
-      const bool new_bias = n_tile != bias_tile;       // warp-uniform; layers with one channel tile load the bias once
-      if (new_bias) {
-        for (int c = etid; c < p.BN; c += 32 * kConvEpiWarps)
-          s_bias[c] = (p.bias && col0 + c < p.Cout) ? __ldg(p.bias + col0 + c) : 0.f;
-        bias_tile = n_tile;
-      }
+      if (u + num_workers < p.num_units) load_bias(u + num_workers, s_bias0 + (size_t)(b ^ 1) * p.BN);
       if (p.tma_res && etid == 0) {
         mbar_arrive_expect_tx(res_bar, (uint32_t)(nblk * blk_bytes));
         for (int bq = 0; bq < nblk; ++bq)
           tma_load_4d(s_stage + (size_t)bq * blk_bytes, &p.tmRes, res_bar, col0 + bq * bc, w0, h0, n0);
       }
-      if (new_bias) named_bar_sync(1, 32 * kConvEpiWarps);
       mbar_wait(&acc_full[b], (i >> 1) & 1);
       tc_fence_after();
       if (p.tma_res) mbar_wait(res_bar, i & 1);

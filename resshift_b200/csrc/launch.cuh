@@ -176,19 +176,19 @@ inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn
       if (f_cg && cg != f_cg && !(f_cg == 2 && m_tiles < 2)) continue;   // a single tile cannot form a pair
       if (cg == 2 && (cand % 16 != 0 || m_tiles < 2)) continue;
       // persistent kernel (conv_persist.cuh): one CTA (pair) per SM walks ceil(units / workers) tiles; the epilogue
-      // (~4600 + 10.4 cycles per column, profiles/r1_s28_persist_sweep.log) hides under the next tile's main loop, so
+      // (~5000 + 3 cycles per column with double-buffered staging, profiles/r1_s38_persist_sweep.log) hides under the next tile's main loop, so
       // a tile costs max(main loop, epilogue) and set-up / first round trip / last epilogue are paid once
       if (allow_persist && 2 * cand <= 512) {
         const long long units_p = (long long)((m_tiles + cg - 1) / cg) * n_tiles;
         const int workers = cg == 2 ? 74 : 148;
         const int sbytes_p = kConvBM * kConvBK * 2 + (cand / cg) * kConvBK * 2;
-        const size_t extra = (size_t)cand * kConvBM * 2 + (size_t)cand * 36 + 1280;
+        const size_t extra = (size_t)2 * cand * kConvBM * 2 + (size_t)cand * 40 + 1280;   // two staging buffers, wsum, two bias slots
         const int st_p = (int)std::min<size_t>(8, ((size_t)227 * 1024 - extra) / (size_t)sbytes_p);
         // (only layers with at least two PIXEL tiles per worker: that is where the model below was calibrated; getting
         // there through many narrow channel tiles would re-read the A operand once per channel tile)
         if ((m_tiles + cg - 1) / cg >= 2 * workers && st_p >= 2) {
-          const double kb_p = std::max(std::max(2.0 * cand, 2.0 * sbytes_p / 128.0), 3000.0 / st_p);
-          const double epi_p = 4600.0 + 10.4 * cand;
+          const double kb_p = std::max(std::max(2.0 * cand, 2.0 * sbytes_p / 128.0), 2600.0 / st_p);
+          const double epi_p = 5000.0 + 3.0 * cand;
           const double rounds = std::ceil((double)units_p / workers);
           const double total = rounds * std::max(num_kb * kb_p, epi_p) + epi_p + 3000.0;
           if (total < bestp.est_cycles) {
@@ -373,7 +373,7 @@ inline int conv_finalize(ConvDesc& d) {
     RS_CHECK(!tc.persist || p.persist, "persistent configuration chosen for an ineligible layer");
     p.num_units = units;
     if (p.persist) {
-      const size_t extra = (size_t)BN * kConvBM * 2 + (size_t)4 * BN * 2 * sizeof(float) + (size_t)BN * sizeof(float) + 256 + 1024;
+      const size_t extra = (size_t)2 * BN * kConvBM * 2 + (size_t)4 * BN * 2 * sizeof(float) + (size_t)2 * BN * sizeof(float) + 256 + 1024;
       const int st = (int)std::min<size_t>(8, ((size_t)227 * 1024 - extra) / (size_t)stage_bytes);
       RS_CHECK(st >= 2, "persistent conv: shared memory budget");
       p.stages = std::min(st, std::max(2, num_kb));
