@@ -82,7 +82,7 @@ def log(msg):
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
-NCU_DRAM_BYTES_PER_GEMM_LAUNCH = 22.67e6
+NCU_DRAM_BYTES_PER_GEMM_LAUNCH = 28.38e6
 
 
 def cpu_reference_images_per_s(steps_T: int, n_images: int, repeats: int):
@@ -280,19 +280,19 @@ def run_gpu(args):
                   "conv1x1 / linear layers) + mlp_fused_sm100_kernel (Swin MLPs)", "bound": "tensor",
         "achieved": conv_tflops, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
         "frac": conv_tflops / peaks["tensor_tflops"],
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 30 GEMM launches of the 64x64 level
-        # captured with `ncu --set full` on this workload (cold caches: ncu flushes between replays);
-        # profiles/r1_s31_gemm_kernels_ncu_full_summary.csv.  Reads are ~ each layer's input (+ residual) once — e.g.
-        # 34.9 MB for a 64x64 160->160 3x3 layer whose input + residual + weights are 42.4 MB (part still L2-resident) —
-        # i.e. no operand is re-read from DRAM (tap / channel-tile re-use is served by the 126 MB L2); outputs mostly
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the first 20 GEMM launches of a forward
+        # (the 64x64 level) captured with `ncu --set full` on this workload (cold caches: ncu flushes between replays);
+        # profiles/r1_s40_gemm_kernels_ncu_full_summary.csv.  Reads are ~ each layer's input (+ residual) once — e.g.
+        # 28-35 MB for a 64x64 160->160 3x3 layer whose input + residual + weights are 42.4 MB (part still L2-resident)
+        # — i.e. no operand is re-read from DRAM (tap / channel-tile re-use is served by the 126 MB L2); outputs mostly
         # stay in L2 (writes ~1 MB / launch).
         "traffic": NCU_DRAM_BYTES_PER_GEMM_LAUNCH if B == BATCH_PER_GPU else None,
         "launches_per_forward": int(nconv.value), "avg_launch_us": pk[0] * 1e3 / max(1, nconv.value),
         "algorithmic_gflop_per_forward": flops.value / 1e9, "peak_source": peaks["source"],
         "per_forward_ms_by_kernel": {"conv_gemm": pk[0], "groupnorm": pk[1], "window_attn": pk[2], "upsample": pk[3]},
-        "traffic_source": "profiles/r1_s31_gemm_kernels_ncu_full_summary.csv (ncu --set full, 30 launches, batch 16)",
-        "tensor_pipe_active_pct_ncu": {"conv_gemm_persist<2> (3x3, 64x64)": 54.0, "conv_gemm<2>": 47.0, "mlp_fused": 23.6,
-                                       "conv_gemm_persist<1> (1x1, epilogue-bound)": 13.3, "conv_gemm<1>": 12.7},
+        "traffic_source": "profiles/r1_s40_gemm_kernels_ncu_full_summary.csv (ncu --set full, 20 launches, batch 16)",
+        "tensor_pipe_active_pct_ncu": {"conv_gemm_persist<2> (3x3, 64x64)": 45.5, "conv_gemm<2>": 43.6, "mlp_fused": 23.0,
+                                       "conv_gemm_persist<1> (1x1, epilogue-bound)": 14.4, "conv_gemm<1>": 8.9},
         "note": "achieved = algorithmic FLOPs of all GEMM launches / sum of their durations, CUDA events around every "
                 "launch of one un-graphed forward on the launching stream (includes inter-launch gaps, so it "
                 "under-states the graph-replayed step)",
