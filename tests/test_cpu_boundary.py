@@ -108,3 +108,37 @@ def test_yaml_loader_resolves_interpolations(tmp_path):
     p.write_text("autoencoder:\n  params:\n    embed_dim: 3\nmodel:\n  params:\n    out_channels: ${autoencoder.params.embed_dim}\n    lq_size: 64\n")
     cfg = load_yaml(p)
     assert cfg.model.params.out_channels == 3 and cfg.model.params["lq_size"] == 64
+
+
+def _tile_config(m_tiles, cout, num_kb):
+    out = (C.c_int32 * 9)()
+    _lib.check(_lib.lib.rs_debug_tile_config(m_tiles, cout, num_kb, out))
+    keys = ("BN", "msub", "stages", "occ", "est_cycles", "cg", "splitk", "persist", "cluster_split")
+    return dict(zip(keys, list(out)))
+
+
+def test_tile_cost_model_invariants_for_the_model_layers():
+    """Host-only: the conv launcher's cost model (launch.cuh) on the benchmark's layer shapes (batch 16).  Checks the
+    structural rules the kernels rely on, not the timing estimates."""
+    shapes = []           # (pixel tiles, Cout, k-blocks)
+    for hw, cin, cout, k in [(64, 160, 160, 3), (64, 480, 160, 3), (64, 320, 320, 3), (64, 192, 576, 1), (64, 192, 192, 1),
+                             (32, 320, 320, 3), (32, 640, 320, 3), (32, 192, 576, 1), (16, 320, 320, 3), (16, 960, 320, 3),
+                             (16, 192, 576, 1), (8, 640, 640, 3), (8, 1280, 640, 3), (8, 192, 192, 1), (8, 640, 192, 1)]:
+        shapes.append((16 * hw * hw // 128, cout, k * k * ((cin + 63) // 64)))
+    for m_tiles, cout, nkb in shapes:
+        tc = _tile_config(m_tiles, cout, nkb)
+        cout16 = (cout + 15) // 16 * 16
+        assert 16 <= tc["BN"] <= 256 and tc["BN"] % 16 == 0 and cout16 % tc["BN"] == 0, tc
+        assert tc["cg"] in (1, 2) and tc["stages"] >= 2 and tc["splitk"] >= 1, tc
+        if tc["persist"]:
+            # only layers with at least two pixel tiles per SM (pair); double-buffered accumulators must fit in TMEM
+            workers = 74 if tc["cg"] == 2 else 148
+            assert (m_tiles + tc["cg"] - 1) // tc["cg"] >= 2 * workers and 2 * tc["BN"] <= 512 and tc["splitk"] == 1, tc
+        if tc["cluster_split"]:
+            assert tc["cg"] == 2 and tc["splitk"] == 2 and (tc["BN"] // 2) % 8 == 0 and not tc["persist"], tc
+        if tc["splitk"] > 1:
+            assert nkb // tc["splitk"] >= 6, tc            # every K range keeps a pipeline's worth of k-blocks
+    # the 64x64 level runs persistent, the few-tile 3x3 layers split K
+    assert _tile_config(512, 160, 27)["persist"] == 1
+    assert _tile_config(8, 640, 90)["splitk"] > 1
+    assert _tile_config(128, 320, 45)["persist"] == 0
