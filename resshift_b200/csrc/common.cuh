@@ -135,29 +135,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// cluster-scope flavours: arrive on a barrier that lives in another CTA of the cluster (address from mapa_u32) with
-// release semantics for this thread's earlier shared-memory writes, and the matching acquire on the waiting side
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
-}
-// same arrival with the default (CTA-scope) release: no cluster-scope memory fence (~2000 cycles, profiles/r1_s21_*).
-// Sufficient when the data the arrival publishes is consumed inside the ARRIVING thread's own CTA (its tensor core
-// reading its own shared memory, made visible by fence.proxy.async) and the remote waiter only needs the count.
+// Arrive on a barrier that lives in another CTA of the cluster (address from mapa_u32) with the default CTA-scope
+// release.  The cluster-scope form (mbarrier.arrive.release.cluster) costs ~2000 cycles per arrival (it fences at
+// cluster scope; profiles/r1_s21 vs r1_s22 timelines) and is not needed when the data the arrival publishes is consumed
+// inside the ARRIVING thread's own CTA (its tensor core reading its own shared memory, made visible by
+// fence.proxy.async) and the remote waiter only needs the count.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
 }
 // Bounded spin: a pipeline bug must not hang the GPU box (that is a strike); after ~2 s of
 // polling the kernel traps instead, which surfaces as a launch failure on the host.
@@ -173,18 +157,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0xFFu) == 0 && global_timer_ns() - t0 > 2000000000ull) {
       printf("rs: mbarrier wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if ((++spins & 0xFFu) == 0 && global_timer_ns() - t0 > 2000000000ull) {
-      printf("rs: mbarrier (cluster) wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
       __trap();
     }
   }
@@ -227,14 +199,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// TMA tile load multicast to every CTA of `cta_mask` (same shared-memory offset and same mbarrier offset in each)
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
-      "[%2], %5;" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
 // 16-byte load from the shared memory of another CTA of the cluster (address from mapa_u32)
 __device__ __forceinline__ float4 ld_shared_cluster_f4(uint32_t cluster_addr) {
   float4 v;
@@ -265,7 +229,6 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // the staged shared memory has been READ by every committed store (it may be reused / the CTA may exit); the global
 // writes themselves complete asynchronously, at the latest at kernel completion
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -330,14 +293,6 @@ __device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t adesc, ui
 // arrive (once the issued MMAs retire) on the barrier at this smem offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(cta_mask)
-               : "memory");
-}
-
-// single-CTA MMAs, arrival delivered to the same barrier offset in every CTA of `cta_mask`
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    smem_u32(bar)),
                "h"(cta_mask)
                : "memory");

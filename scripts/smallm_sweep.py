@@ -1,4 +1,7 @@
-"""Sweep tile configurations for the low-resolution (few-tile) conv layers: time per launch via CUDA events."""
+"""SUPERSEDED by scripts/conv_sweep.py (this one times from the host, one launch at a time, and is launch-bound for
+the small layers it was meant to study; kept because profiles/r1_s12_smallm_sweep.log was produced by it).
+
+Sweep tile configurations for the low-resolution (few-tile) conv layers: time per launch via CUDA events."""
 import ctypes as C
 import itertools
 import os
