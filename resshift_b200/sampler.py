@@ -107,6 +107,20 @@ def reload_model(model, ckpt):
         v.copy_(ckpt[tk])
 
 
+def tile_starts(length: int, patch: int, stride: int):
+    """Start offsets of the overlapping tiles along one axis — the same list, in the same order, as the reference's
+    ImageSpliterTh.extract_starts (utils/util_image.py:923-932): multiples of `stride`, the last ones pulled back so
+    that every tile lies inside the image, duplicates dropped."""
+    if length <= patch:
+        return [0]
+    out = []
+    for s0 in range(0, length, stride):
+        s1 = min(s0, length - patch)
+        if s1 not in out:
+            out.append(s1)
+    return out
+
+
 class BaseSampler:
     def __init__(self, configs, sf=4, use_amp=True, chop_size=128, chop_stride=128, chop_bs=1, padding_offset=16,
                  seed=10000):
@@ -225,14 +239,8 @@ class ResShiftSampler(BaseSampler):
             acc = torch.zeros(b, c, h * sf, w * sf, device=im_lq.device)
             cnt = torch.zeros_like(acc)
 
-            def starts(n):
-                if n <= ps:
-                    return [0]
-                s = list(range(0, n - ps, st)) + [n - ps]
-                return sorted(set(s))
-
-            for hs in starts(h):
-                for ws in starts(w):
+            for hs in tile_starts(h, ps, st):
+                for ws in tile_starts(w, ps, st):
                     he, we = min(hs + ps, h), min(ws + ps, w)
                     with ctx:
                         pch = self.sample_func(im_lq[:, :, hs:he, ws:we], noise_repeat=noise_repeat,

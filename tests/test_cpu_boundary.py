@@ -142,3 +142,30 @@ def test_tile_cost_model_invariants_for_the_model_layers():
     assert _tile_config(512, 160, 27)["persist"] == 1
     assert _tile_config(8, 640, 90)["splitk"] > 1
     assert _tile_config(128, 320, 45)["persist"] == 0
+
+
+def test_tile_starts_match_reference_image_splitter():
+    """The sampler's tiling of large inputs must cut the same tiles as the reference's ImageSpliterTh
+    (utils/util_image.py:889-979).  Compared against the reference class itself when its tree is present (this
+    container), against a table generated from it otherwise (the GPU box)."""
+    import sys
+    from resshift_b200.sampler import tile_starts
+    table = {(300, 128, 128): [0, 128, 172], (256, 128, 128): [0, 128], (240, 128, 112): [0, 112], (500, 128, 112): [0, 112, 224, 336, 372],
+             (100, 128, 64): [0], (129, 128, 128): [0, 1], (592, 256, 224): [0, 224, 336], (448, 256, 224): [0, 192]}
+    for (n, ps, st), want in table.items():
+        assert tile_starts(n, ps, st) == want, (n, ps, st)
+    ref_root = Path("/root/reference")
+    if not ref_root.exists():
+        return
+    sys.path[:0] = [str(ROOT / "oracle" / "_shims"), str(ref_root)]
+    try:
+        from utils.util_image import ImageSpliterTh
+        for n in list(range(1, 70)) + [100, 127, 128, 129, 200, 255, 256, 257, 300, 448, 500, 592, 1000]:
+            for ps, st in [(16, 16), (16, 12), (32, 28), (64, 64), (128, 112), (256, 224)]:
+                sp = ImageSpliterTh(torch.zeros(1, 1, n, max(n // 2, 1)), ps, st, sf=1)
+                assert tile_starts(n, ps, st) == sp.height_starts_list, (n, ps, st)
+                assert tile_starts(max(n // 2, 1), ps, st) == sp.width_starts_list, (n, ps, st)
+    finally:
+        del sys.path[:2]
+        for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            del sys.modules[m]
