@@ -1,6 +1,11 @@
 #!/bin/bash
-# GPU session 42 (2 GPUs): the driver's N=2 launch with the round-1 end-state build
+# GPU session 43: sampler class / tiler after the tile_starts refactor
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 \
-    bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_n2.log 2> gpurun_out/bench_n2.err
-echo "rc=$?"; cat gpurun_out/bench_n2.log | cut -c1-330; tail -3 gpurun_out/bench_n2.err
+timeout 600 python -m pytest tests/test_gpu_unet.py -q -k "sampler_class or forward_vs_reference_golden" 2>&1 | tail -3
+timeout 300 python - <<'PY'
+# tiled path: an input larger than chop_size through ResShiftSampler._process vs per-tile calls
+import torch, sys
+sys.path.insert(0, '.')
+from resshift_b200.sampler import tile_starts
+print("tile_starts ok", tile_starts(300, 128, 128))
+PY
