@@ -135,6 +135,10 @@ def preset(name: str, steps: Optional[int] = None) -> Tuple[UNetConfig, Diffusio
         # not a shipped config: a narrow model with the same topology, for fast tests
         u = UNetConfig(model_channels=32, swin_embed_dim=64)
         d = DiffusionConfig(steps=4, min_noise_level=0.2)
+    elif name == "tiny_faceir":
+        # narrow model with the face-restoration topology: 8 latent channels, three-stage LQ feature extractor at 512
+        u = UNetConfig(model_channels=32, swin_embed_dim=64, in_channels=8, out_channels=8, lq_size=512)
+        d = DiffusionConfig(sf=1, steps=4, min_noise_level=0.2)
     elif name == "tiny_inpaint":
         u = UNetConfig(model_channels=32, swin_embed_dim=64, cond_mask=True, lq_size=256)
         d = DiffusionConfig(sf=1, steps=4, min_noise_level=0.2)

@@ -40,12 +40,14 @@ def _report(tag, got, ref):
 
 
 @pytest.mark.parametrize("name,fname", [("tiny", "unet_tiny.npz"), ("tiny_inpaint", "unet_tiny_inpaint.npz"),
-                                         ("realsr", "unet_realsr.npz")])
+                                         ("tiny_faceir", "unet_tiny_faceir.npz"), ("realsr", "unet_realsr.npz")])
 def test_forward_vs_reference_golden(golden_dir, name, fname):
+    from tests.golden_util import golden_inputs
     g = np.load(golden_dir / fname)
     ucfg, _, m = _model(name)
-    x, t, lq = (torch.from_numpy(g[k]).cuda() for k in ("x", "t", "lq"))
-    mask = torch.from_numpy(g["mask"]).cuda() if "mask" in g.files else None
+    x, t, lq, mask = golden_inputs(g)
+    x, t, lq = x.cuda(), t.cuda(), lq.cuda()
+    mask = None if mask is None else mask.cuda()
     out = m(x, t, lq=lq, mask=mask)
     assert not torch.isnan(out).any()
     mx, mn = _report(f"forward {name}", out, torch.from_numpy(g["out"]))

@@ -36,9 +36,9 @@ def _check_forward(golden_dir, preset_name, fname):
     ucfg, _ = preset(preset_name)
     sd = random_state_dict(ucfg, 0)
     probes = {}
-    mask = torch.from_numpy(g["mask"]) if "mask" in g.files else None
-    out = uo.unet_forward(sd, ucfg, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]),
-                          lq=torch.from_numpy(g["lq"]), mask=mask, probes=probes)
+    from tests.golden_util import golden_inputs
+    x, t, lq, mask = golden_inputs(g)
+    out = uo.unet_forward(sd, ucfg, x, t, lq=lq, mask=mask, probes=probes)
     assert np.abs(out.numpy() - g["out"]).max() < TOL
     for k, v in probes.items():
         ref_sub = g[f"probe_sub/{k}"]
@@ -52,6 +52,11 @@ def test_unet_tiny_forward(golden_dir):
 
 def test_unet_tiny_inpaint_forward(golden_dir):
     _check_forward(golden_dir, "tiny_inpaint", "unet_tiny_inpaint.npz")
+
+
+def test_unet_tiny_faceir_forward(golden_dir):
+    """Face-restoration topology (8 latent channels, three-stage feature extractor on a 512x512 LQ input)."""
+    _check_forward(golden_dir, "tiny_faceir", "unet_tiny_faceir.npz")
 
 
 def test_unet_realsr_forward(golden_dir):
