@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_unet.py -q -k "forward_vs_reference_golden" 2>&1 | tail -4
+timeout 300 python scripts/bench_other_tasks.py 2>&1 | tee gpurun_out/bench_other_tasks.log | tail -4
