@@ -203,3 +203,32 @@ def test_tiled_processing_matches_reference_splitter_average():
         for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
             del sys.modules[m]
     assert got.shape == want.shape and torch.allclose(got, want, atol=1e-6)
+
+
+def test_overlay_resolves_reference_module_names_to_this_package(tmp_path):
+    """`python -m resshift_b200.launch <script>` must make `sampler`, `models.unet`, `models.script_util` resolve to this
+    package while every other `models.*` module still comes from the reference tree (namespace package), exactly as an
+    unmodified reference entry script imports them."""
+    import subprocess
+    import sys
+    ref_root = Path("/root/reference")
+    if not ref_root.exists():
+        pytest.skip("reference tree not present")
+    probe = tmp_path / "probe_entry.py"
+    probe.write_text(
+        "import sampler, models.unet, models.script_util\n"
+        "import models.basic_ops as ref_ops\n"
+        "print('sampler=' + sampler.ResShiftSampler.__module__)\n"
+        "print('unet=' + models.unet.UNetModelSwin.__module__)\n"
+        "print('diffusion=' + models.script_util.create_gaussian_diffusion.__module__)\n"
+        "print('ref_ops=' + ref_ops.__file__)\n")
+    # the probe sits in a scratch directory; the reference tree is appended the way its own scripts would see it
+    env = dict(**__import__("os").environ, PYTHONPATH=str(ref_root) + ":" + str(ROOT / "oracle" / "_shims"))
+    out = subprocess.run([sys.executable, "-m", "resshift_b200.launch", str(probe)], cwd=str(ROOT), env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = dict(line.split("=", 1) for line in out.stdout.strip().splitlines() if "=" in line)
+    assert got["sampler"] == "resshift_b200.sampler"
+    assert got["unet"] == "resshift_b200.models.unet"
+    assert got["diffusion"] == "resshift_b200.models.script_util"
+    assert got["ref_ops"].startswith(str(ref_root))
