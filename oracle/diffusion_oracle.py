@@ -53,7 +53,7 @@ def p_sample_loop(model: Callable, z_y: torch.Tensor, noises: List[torch.Tensor]
     f32 = lambda a, i: torch.tensor(float(np.float32(a[i])))   # _extract_into_tensor casts to fp32 (:102)
     x = z_y + f32(kappa * tabs["sqrt_etas"], T - 1) * noises[0]
     for k, i in enumerate(range(T - 1, -1, -1)):
-        t = torch.full((z_y.shape[0],), i, dtype=torch.long)
+        t = torch.full((z_y.shape[0],), i, dtype=torch.long, device=z_y.device)
         std_in = torch.sqrt(f32(tabs["etas"], i) * kappa ** 2 + 1)
         pred = model(x / std_in, t).float()
         mean = f32(tabs["coef1"], i) * x + f32(tabs["coef2"], i) * pred

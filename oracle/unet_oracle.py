@@ -26,7 +26,7 @@ SD = Dict[str, torch.Tensor]
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
     """reference models/basic_ops.py:99-117 — [cos | sin] halves, fp32."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
@@ -83,7 +83,7 @@ def swin_block(x, sd: SD, p: str, heads: int, win: int, shift: int):
     # window_partition (reference :35-47)
     yw = y.view(b, c, h // win, win, w // win, win).permute(0, 2, 4, 3, 5, 1).reshape(-1, win * win, c)
     # the reference always rebuilds the mask from the runtime size (:262-265); it is all-zero for shift 0
-    mask = shifted_window_mask(h, w, win, shift) if shift else None
+    mask = shifted_window_mask(h, w, win, shift).to(y.device) if shift else None
     aw = window_attention(yw, sd, f"{p}.attn", heads, mask)
     # window_reverse (reference :49-63)
     y = aw.view(b, h // win, w // win, win, win, c).permute(0, 5, 1, 3, 2, 4).reshape(b, c, h, w)
@@ -132,7 +132,8 @@ def _run_block(h, emb, sd: SD, prefix: str, layers, cfg: UNetConfig):
 
 @torch.no_grad()
 def unet_forward(sd: SD, cfg: UNetConfig, x, timesteps, lq=None, mask=None, probes: Optional[dict] = None):
-    """reference models/unet.py:865-895.  All tensors NCHW fp32 on CPU."""
+    """reference models/unet.py:865-895.  All tensors NCHW fp32, on one device (CPU for the parity tests; bench.py's
+    informational `gpu_library_baseline` runs the same functions on CUDA under fp16 autocast)."""
     emb = timestep_embedding(timesteps, cfg.model_channels)
     emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])

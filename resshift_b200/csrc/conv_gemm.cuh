@@ -42,6 +42,8 @@ struct ConvParams {
   int tap_dh[kMaxTaps];
   int tap_dw[kMaxTaps];
   int kchunks;           // ceil(Cin / 64)
+  int tail_k16;          // 16-channel MMA steps of the LAST 64-channel chunk that hold real channels (1..4): the zero-filled
+                         // remainder of a partial chunk (Cin = 160 -> 32 of 64, Cin = 8 -> 8 of 64) is not multiplied
   int w_tap_stride;      // K offset between consecutive taps in the weight matrix (= Cin_pad)
   int bw, bh, bn;        // pixel box of a tile, bw*bh*bn == 128
   int tiles_w, tiles_h, tiles_n;
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
     const uint32_t b_off = (uint32_t)(p.msub * a_bytes);
     int stage = 0;
     uint32_t phase = 0;
+    int kc = kb_begin % p.kchunks;                    // 64-channel chunk index inside the current tap
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
@@ -219,11 +222,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
       const uint64_t adesc = umma_desc_sw128(sa);
       const uint64_t bdesc = umma_desc_sw128(sa + b_off);
       const uint32_t acc0 = kb != 0 ? 1u : 0u;
+      const int ksteps = (kc == p.kchunks - 1) ? p.tail_k16 : kConvBK / 16;   // skip the zero-filled tail of a partial chunk
+      if (++kc == p.kchunks) kc = 0;
       if constexpr (kCG == 2) {
         if (el) {
           umma_f16_cg2(tmem_base, adesc, bdesc, idesc, acc0);
 #pragma unroll
-          for (int k = 1; k < kConvBK / 16; ++k) umma_f16_cg2(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+          for (int k = 1; k < kConvBK / 16; ++k) if (k < ksteps) umma_f16_cg2(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
           umma_commit_cg2(&empty_bar[stage], pair_mask);                    // frees the stage in BOTH CTAs
           if (kb == num_kb - 1) umma_commit_cg2(tmem_full_bar, pair_mask);  // accumulators of both CTAs complete
         }
@@ -232,12 +237,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
           // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
           umma_f16(tmem_base, adesc, bdesc, idesc, acc0);
 #pragma unroll
-          for (int k = 1; k < kConvBK / 16; ++k) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+          for (int k = 1; k < kConvBK / 16; ++k) if (k < ksteps) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
           if (p.msub == 2) {
             const uint64_t adesc1 = umma_desc_sw128(sa + a_bytes);
             umma_f16(tmem_base + p.BN, adesc1, bdesc, idesc, acc0);
 #pragma unroll
-            for (int k = 1; k < kConvBK / 16; ++k) umma_f16(tmem_base + p.BN, adesc1 + 2 * k, bdesc + 2 * k, idesc, 1u);
+            for (int k = 1; k < kConvBK / 16; ++k) if (k < ksteps) umma_f16(tmem_base + p.BN, adesc1 + 2 * k, bdesc + 2 * k, idesc, 1u);
           }
           umma_commit(&empty_bar[stage]);                 // frees this smem stage when the MMAs retire
           if (kb == num_kb - 1) umma_commit(tmem_full_bar);  // accumulator complete

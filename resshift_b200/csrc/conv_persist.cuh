@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
       mbar_wait(&acc_empty[b], ((i >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)(b * p.BN);
+      int kc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -137,11 +138,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
         const uint64_t adesc = umma_desc_sw128(sa);
         const uint64_t bdesc = umma_desc_sw128(sa + (uint32_t)a_bytes);
         const uint32_t acc0 = kb != 0 ? 1u : 0u;
+        const int ksteps = (kc == p.kchunks - 1) ? p.tail_k16 : kConvBK / 16;   // skip the zero-filled tail of a partial chunk
+        if (++kc == p.kchunks) kc = 0;
         if constexpr (kCG == 2) {
           if (el) {
             umma_f16_cg2(d, adesc, bdesc, idesc, acc0);
 #pragma unroll
-            for (int k = 1; k < kConvBK / 16; ++k) umma_f16_cg2(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+            for (int k = 1; k < kConvBK / 16; ++k) if (k < ksteps) umma_f16_cg2(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
             umma_commit_cg2(&empty_bar[stage], 3);
             if (kb == num_kb - 1) umma_commit_cg2(&acc_full[b], 3);
           }
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
           if (el) {
             umma_f16(d, adesc, bdesc, idesc, acc0);
 #pragma unroll
-            for (int k = 1; k < kConvBK / 16; ++k) umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+            for (int k = 1; k < kConvBK / 16; ++k) if (k < ksteps) umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
             umma_commit(&empty_bar[stage]);
             if (kb == num_kb - 1) umma_commit(&acc_full[b]);
           }

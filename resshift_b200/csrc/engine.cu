@@ -46,6 +46,7 @@ struct rs_engine {
   std::map<std::string, int> index;
   size_t arena_bytes = 0;
   uint8_t* arena = nullptr;
+  unsigned long long weights_epoch = 0;     // bumped by every rs_unet_load_param: tables derived from weights (FiLM) go stale
   // concatenated emb_layers ("FiLM") matrix: rows = sum 2*Cout over ResBlocks, K = time_embed_dim
   size_t film_w_off = 0, film_b_off = 0;
   int film_rows = 0;
@@ -300,6 +301,11 @@ struct rs_plan {
   float* out_f32 = nullptr;  // model output (fp32 NCHW), inside the state region
   bool bound = false;
   int launches = 0;
+  // The schedule tables and the FiLM table live in this plan's workspace and are shared by rs_plan_forward (FiLM rows
+  // 0..B-1 for the caller's timesteps) and by every sampler of the plan (rows 0..T-1 for its schedule): whoever wrote them
+  // last owns them.  A sampler re-derives them when it is not the owner or when the weights changed since (weights_epoch).
+  const void* table_owner = nullptr;
+  unsigned long long table_epoch = ~0ull;
 
   int new_tensor(size_t bytes, bool persistent = false) {
     Tensor t; t.bytes = align_up(bytes, 256); t.persistent = persistent;
@@ -764,10 +770,27 @@ struct Prof {
   ~Prof() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
 };
 
+// RS_SKIP_KINDS (timing ablation only — results are garbage): bit 0 conv3x3, 1 conv1x1 / linear, 2 GroupNorm, 3 window
+// attention, 4 upsample, 5 fused MLP.  The time a kernel family really costs inside the graph-replayed step is the
+// difference between the full step and the step without it (per-launch events and ncu both over-state small kernels).
+inline bool op_skipped(const Op& op) {
+  static const int skip = env_int("RS_SKIP_KINDS", 0);
+  if (!skip) return false;
+  switch (op.kind) {
+    case OP_CONV: return (skip >> (op.conv.ksize == 3 ? 0 : 1)) & 1;
+    case OP_GN: return (skip >> 2) & 1;
+    case OP_ATTN: return (skip >> 3) & 1;
+    case OP_UPSAMPLE: return (skip >> 4) & 1;
+    case OP_MLP: return (skip >> 5) & 1;
+  }
+  return false;
+}
+
 int run_ops(rs_plan& P, const std::vector<Op>& ops, const float* film_base, long long film_sN, cudaStream_t st,
             Prof* prof = nullptr) {
   for (const Op& op : ops) {
     int rc = 0;
+    if (op_skipped(op)) { if (prof) { cudaEventRecord(prof->get(), st); prof->kind.push_back((int)op.kind); cudaEventRecord(prof->get(), st); } continue; }
     if (prof) { cudaEventRecord(prof->get(), st); prof->kind.push_back((int)op.kind); }
     switch (op.kind) {
       case OP_CONV: rc = conv_launch(op.conv, st); break;
@@ -889,6 +912,7 @@ int rs_unet_load_param(rs_engine* e, const char* name, const float* src, void* s
   const Param* p = e->find(name);
   RS_CHECK(p != nullptr, std::string("unknown parameter ") + name);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ++e->weights_epoch;
   if (p->bytes == 0) return 0;      // derived buffers (relative_position_index, attn_mask) are not stored
   if (p->role == R_CONV3 || p->role == R_CONV1 || p->role == R_LINEAR) {
     const int O = p->shape[0], I = p->shape[1];
@@ -946,6 +970,7 @@ int rs_plan_forward(rs_plan* p, const float* x, const float* timesteps, const fl
   RS_CHECK(p && p->bound, "plan is not bound");
   RS_CHECK(x && timesteps && lq && out, "null tensor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->table_owner = nullptr;                       // FiLM rows 0..B-1 are overwritten below
   int rc = run_embedding(*p, timesteps, p->B, st); if (rc) return rc;
   rc = pack_lq_and_input(*p, x, lq, mask, nullptr, 0, st); if (rc) return rc;
   const float* film = reinterpret_cast<const float*>(p->ws + p->off_film);
@@ -963,6 +988,7 @@ int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const fl
                     double* ms_by_kind, double* conv_flops, int32_t* n_conv_launches, void* stream) {
   RS_CHECK(p && p->bound && ms_by_kind, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->table_owner = nullptr;
   int rc = run_embedding(*p, timesteps, p->B, st); if (rc) return rc;
   rc = pack_lq_and_input(*p, x, lq, mask, nullptr, 0, st); if (rc) return rc;
   Prof prof;
@@ -995,6 +1021,7 @@ int rs_plan_profile_ops(rs_plan* p, const float* x, const float* timesteps, cons
                         double* ms, char* desc, int desc_stride, int cap, int32_t* n_ops, void* stream) {
   RS_CHECK(p && p->bound && ms && desc && n_ops, "bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->table_owner = nullptr;
   int rc = run_embedding(*p, timesteps, p->B, st); if (rc) return rc;
   rc = pack_lq_and_input(*p, x, lq, mask, nullptr, 0, st); if (rc) return rc;
   Prof prof;
@@ -1060,7 +1087,6 @@ struct rs_sampler {
   double kappa = 0;
   std::vector<float> coef1, coef2, stdv, in_scale, tsteps;
   float prior_coef = 0;
-  bool tables_uploaded = false;
   float* tap_pred = nullptr; float* tap_sample = nullptr;
   cudaGraphExec_t graph = nullptr;
   cudaStream_t cap_stream = nullptr;     // capture happens on a private stream (the legacy default stream cannot capture)
@@ -1106,8 +1132,8 @@ int sampler_enqueue(rs_sampler& S, const float* z_y, const float* noises, const 
 int sampler_prepare(rs_sampler& S, cudaStream_t st) {
   // tables + the FiLM table of all T steps (depends on the timestep only: reference models/unet.py:874,
   // models/respace.py:60-63) — computed once, outside any graph capture.
-  if (S.tables_uploaded) return 0;
   rs_plan& P = *S.p;
+  if (P.table_owner == &S && P.table_epoch == P.e->weights_epoch) return 0;
   float* tab = reinterpret_cast<float*>(P.ws + P.off_tables);
   RS_CUDA_OK(cudaMemcpyAsync(tab, S.coef1.data(), S.T * 4, cudaMemcpyHostToDevice, st));
   RS_CUDA_OK(cudaMemcpyAsync(tab + 1024, S.coef2.data(), S.T * 4, cudaMemcpyHostToDevice, st));
@@ -1117,7 +1143,7 @@ int sampler_prepare(rs_sampler& S, cudaStream_t st) {
   RS_CUDA_OK(cudaMemcpyAsync(ts, S.tsteps.data(), S.T * 4, cudaMemcpyHostToDevice, st));
   int rc = run_embedding(P, ts, S.T, st); if (rc) return rc;
   RS_CUDA_OK(cudaStreamSynchronize(st));     // host vectors must outlive the copies; one-time setup cost
-  S.tables_uploaded = true;
+  P.table_owner = &S; P.table_epoch = P.e->weights_epoch;
   return 0;
 }
 
@@ -1150,6 +1176,7 @@ int rs_sampler_create(rs_plan* p, int steps, const double* sqrt_etas, double kap
   return 0;
 }
 void rs_sampler_destroy(rs_sampler* s) {
+  if (s && s->p && s->p->table_owner == s) s->p->table_owner = nullptr;
   if (s && s->graph) cudaGraphExecDestroy(s->graph);
   if (s && s->cap_stream) cudaStreamDestroy(s->cap_stream);
   delete s;

@@ -284,6 +284,10 @@ inline int conv_finalize(ConvDesc& d) {
   p.Hout = Hout; p.Wout = Wout; p.Nimg = N; p.Cout = d.Cout;
   p.num_taps = d.ksize * d.ksize;
   p.kchunks = (d.in.C + kConvBK - 1) / kConvBK;
+  {
+    const int tail = d.in.C - (p.kchunks - 1) * kConvBK;                 // real channels of the last 64-channel chunk
+    p.tail_k16 = env_int("RS_CONV_TAILSKIP", 1) ? (tail + 15) / 16 : kConvBK / 16;
+  }
   p.w_tap_stride = d.ipad;
   RS_CHECK(d.ipad % 8 == 0 && d.ipad >= d.in.C, "weight channel padding");
   // pixel box

@@ -191,7 +191,28 @@ class ResShiftDiffusion:
     def _native_ok(self, model, clip_denoised, denoised_fn, model_kwargs) -> bool:
         return (isinstance(model, UNetModelSwin) and self.model_mean_type == ModelMeanType.START_X
                 and not clip_denoised and denoised_fn is None and self.normalize_input and self.latent_flag
-                and model_kwargs is not None and "lq" in model_kwargs)
+                and model_kwargs is not None and "lq" in model_kwargs
+                and 2 <= self.num_timesteps <= 64)       # rs_sampler_create: 2 <= T <= FiLM-table rows of a plan
+
+    @staticmethod
+    def _check_native_inputs(model: UNetModelSwin, z_y, lq, mask):
+        """Same contract as UNetModelSwin.forward (reference models/unet.py:865-882 asserts `mask is not None` iff
+        cond_mask): the library receives raw pointers, so every shape is checked here."""
+        cfg = model.cfg
+        B, Cc, H, W = z_y.shape
+        if Cc != cfg.in_channels:
+            raise ValueError(f"latent has {Cc} channels, the model expects {cfg.in_channels}")
+        exp_lq = (B, 3, H << cfg.fe_stages, W << cfg.fe_stages)
+        if tuple(lq.shape) != exp_lq:
+            raise ValueError(f"lq must have shape {exp_lq}, got {tuple(lq.shape)}")
+        if cfg.cond_mask:
+            if mask is None:
+                raise ValueError("this model is mask-conditioned (cond_mask=True): pass model_kwargs['mask']")
+            exp_m = (B, 1) + exp_lq[2:]
+            if tuple(mask.shape) != exp_m:
+                raise ValueError(f"mask must have shape {exp_m}, got {tuple(mask.shape)}")
+        elif mask is not None:
+            raise ValueError("a mask was given but the model is not mask-conditioned (cond_mask=False)")
 
     def native_sampler(self, model: UNetModelSwin, batch, height, width):
         plan = model.plan(batch, height, width)
@@ -230,6 +251,7 @@ class ResShiftDiffusion:
             lq = model_kwargs["lq"].float().contiguous()
             mask = model_kwargs.get("mask", None)
             mask = mask.float().contiguous() if mask is not None else None
+            self._check_native_inputs(model, zf, lq, mask)
             final = torch.empty_like(zf)
             preds = torch.empty((T,) + tuple(zf.shape), dtype=torch.float32, device=zf.device)
             samples = torch.empty_like(preds)
@@ -290,7 +312,11 @@ class ResShiftDiffusion:
         bufs = getattr(plan, "_io", None)
         lq_in = model_kwargs["lq"]
         mask_in = model_kwargs.get("mask", None)
-        if bufs is None or bufs["lq"].shape != lq_in.shape or (mask_in is None) != (bufs["mask"] is None):
+        self._check_native_inputs(model, z_y, lq_in, mask_in)
+        if tuple(noises.shape) != (self.num_timesteps + 1,) + tuple(z_y.shape):
+            raise ValueError(f"noises must have shape {(self.num_timesteps + 1,) + tuple(z_y.shape)}, got {tuple(noises.shape)}")
+        if (bufs is None or bufs["lq"].shape != lq_in.shape or (mask_in is None) != (bufs["mask"] is None)
+                or bufs["noise"].shape != noises.shape):
             bufs = {"zy": torch.empty(B, Cc, H, W, dtype=torch.float32, device=z_y.device),
                     "noise": torch.empty_like(noises),
                     "lq": torch.empty(lq_in.shape, dtype=torch.float32, device=z_y.device),

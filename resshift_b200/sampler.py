@@ -188,18 +188,20 @@ class BaseSampler:
 
     # -- NCCL plumbing the north-star asks for (the reference has each rank read the checkpoint) --------
     def broadcast_weights(self, src: int = 0):
+        """One flat NCCL broadcast of every parameter from rank `src` (resshift_b200.parallel), then repack."""
         if self.num_gpus > 1:
-            for p in self.model.parameters():
-                dist.broadcast(p.data, src=src)
+            from .parallel import broadcast_state_dict
+            broadcast_state_dict({k: p.data for k, p in self.model.named_parameters()}, src=src)
             self.model.pack_weights(force=True)
 
-    def gather_results(self, local: torch.Tensor) -> Optional[torch.Tensor]:
-        """All ranks call; every rank gets the concatenated batch (NCCL all_gather over NVLink)."""
+    def gather_results(self, local: torch.Tensor, batch: Optional[int] = None) -> Optional[torch.Tensor]:
+        """All ranks call; every rank gets the global batch in order (NCCL all_gather over NVLink).  `batch` = global
+        batch size; shards follow the reference's ceil(bs / world) slicing (sampler.py:273-277), so trailing ranks may
+        hold fewer images or none (resshift_b200.parallel.gather_shards pads and trims)."""
         if self.num_gpus == 1:
             return local
-        outs = [torch.empty_like(local) for _ in range(self.num_gpus)]
-        dist.all_gather(outs, local.contiguous())
-        return torch.cat(outs, dim=0)
+        from .parallel import gather_shards
+        return gather_shards(local.contiguous(), local.shape[0] * self.num_gpus if batch is None else batch)
 
 
 class ResShiftSampler(BaseSampler):

@@ -284,6 +284,28 @@ def test_groupnorm(C, cfg):
     assert st["nan"] == 0 and st["max_abs"] <= _tol(ref), st
 
 
+@pytest.mark.parametrize("C,H", [(160, 64), (192, 16), (640, 8)])
+def test_groupnorm_large_mean(C, H):
+    """Stress case for the variance: per-group mean >> std (mean 30, std 0.5; fp16 storage of the input is part of the
+    operand, so the fp32 reference sees the same rounded values).  A single-pass E[x^2] - mean^2 in fp32 loses the
+    variance to cancellation here; the statistics are kept as (mean, M2) around local means instead.
+    reference: GroupNorm32 = F.group_norm in fp32 (models/basic_ops.py:15-17)."""
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    N = 2
+    x = G.nhwc16(torch.randn(N, C, H, H, device="cuda", generator=g) * 0.5 + 30.0)
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(C, device="cuda", generator=g)
+    y = torch.empty_like(x)
+    scratch = torch.empty(G.L.rs_op_groupnorm_scratch_floats(N, H, H, C), dtype=torch.float32, device="cuda")
+    _lib.check(G.L.rs_op_groupnorm(x.data_ptr(), N, H, H, C, C, gamma.data_ptr(), beta.data_ptr(), None, 0, 0,
+                                   y.data_ptr(), C, scratch.data_ptr(), G.stream()))
+    torch.cuda.synchronize()
+    ref = F.group_norm(G.nchw32(x), 32, gamma, beta, eps=1e-5)
+    st = G.err_stats(G.nchw32(y), ref)
+    print(f"[groupnorm stress] C={C} H={H}: {st}")
+    assert st["nan"] == 0 and st["max_abs"] <= _tol(ref), st
+
+
 @pytest.mark.parametrize("impl", ["mma", "simt"])
 @pytest.mark.parametrize("shift", [0, 4])
 @pytest.mark.parametrize("hw", [(8, 8), (16, 32), (64, 64)])

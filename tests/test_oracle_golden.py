@@ -63,6 +63,13 @@ def test_unet_realsr_forward(golden_dir):
     _check_forward(golden_dir, "realsr", "unet_realsr.npz")
 
 
+@pytest.mark.parametrize("name,fname", [("faceir", "unet_faceir.npz"), ("inpaint", "unet_inpaint.npz"),
+                                         ("realsr", "unet_realsr_64x128.npz"), ("tiny", "unet_tiny_128x64.npz")])
+def test_unet_round2_fixtures(golden_dir, name, fname):
+    """Full-width face-restoration / inpainting topologies and non-square latents, reference-generated."""
+    _check_forward(golden_dir, name, fname)
+
+
 @pytest.mark.parametrize("name,steps,T", [("realsr", None, 15), ("realsr_journal", None, 4), ("realsr_journal", 15, 15)])
 def test_schedule_tables(golden_dir, name, steps, T):
     g = np.load(golden_dir / f"schedule_{name}_T{T}.npz")
@@ -91,8 +98,9 @@ def _check_loop(golden_dir, preset_name, steps, fname):
     sd = random_state_dict(ucfg, 0)
     se = do.eta_schedule(d.steps, d.min_noise_level, d.etas_end, d.kappa, d.schedule_kwargs["power"])
     tabs = do.schedule_tables(se, d.kappa)
-    y = torch.from_numpy(g["y"])
-    noises = [torch.from_numpy(n) for n in g["noises"]]
+    from tests.golden_util import golden_loop_inputs
+    y, noises = golden_loop_inputs(g)
+    noises = list(noises)
     rec = []
     final = do.p_sample_loop(lambda x, t: uo.unet_forward(sd, ucfg, x, t, lq=y), y, noises, tabs, d.kappa, rec)
     for key in g.files:
@@ -109,3 +117,7 @@ def test_loop_tiny(golden_dir):
 
 def test_loop_realsr_15(golden_dir):
     _check_loop(golden_dir, "realsr", 15, "loop_realsr_T15.npz")
+
+
+def test_loop_realsr_15_batch2(golden_dir):
+    _check_loop(golden_dir, "realsr", 15, "loop_realsr_T15_b2.npz")
