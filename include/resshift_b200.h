@@ -123,14 +123,19 @@ int rs_op_pack_conv_weight(const float* src_oihw, void* dst_f16, int O, int I, i
 int rs_op_conv2d(const void* x, int N, int H, int W, int C, int ld, const void* w_packed, int Ipad, const float* bias,
                  int Cout, int ksize, int stride, const void* residual, int res_ld, void* out, int out_ld,
                  float* out_f32_nchw, int act, int bn, void* stream);
-/* conv2d + GroupNorm partial statistics of its output (part[N][slots][cstride][2] at channel offset coff) */
+/* conv2d + GroupNorm statistics of its output: part[N][slots][cstride][2] = (mean, M2) of the stored values per image /
+ * 128-pixel tile slot / channel at channel offset coff; with gstat + counter (uint32[N], zeroed by the caller) the last
+ * CTA of each image also writes gstat[N][32][2] = (group mean, group rstd) once slots * expected_channels channel-slots
+ * arrived (expected_channels = 0: cstride).  reference: the GroupNorm32 that follows every conv (models/basic_ops.py:15-17) */
 int rs_op_conv2d_stats(const void* x, int N, int H, int W, int C, int ld, const void* w_packed, int Ipad, const float* bias,
                        int Cout, int ksize, int stride, const void* residual, int res_ld, void* out, int out_ld, int act,
-                       int bn, float* part, int cstride, int coff, int32_t* slots_out, void* stream);
+                       int bn, float* part, int cstride, int coff, int32_t* slots_out, float* gstat, void* counter,
+                       int expected_channels, void* stream);
 /* conv2d that may split its K loop over several CTAs (layers with few output tiles); scratch: 8*N*Ho*Wo*Cout floats */
 int rs_op_conv2d_splitk(const void* x, int N, int H, int W, int C, int ld, const void* w_packed, int Ipad, const float* bias,
                         int Cout, int ksize, int stride, const void* residual, int res_ld, void* out, int out_ld, int act,
-                        float* part, int cstride, int coff, float* scratch, int32_t* splits_out, void* stream);
+                        float* part, int cstride, int coff, float* scratch, int32_t* splits_out, float* gstat, void* counter,
+                        void* stream);
 /* profiling aid: `iters` launches of the same conv; per-CTA timeline of the last one in dbg (8 x u64 per CTA) */
 int rs_op_conv2d_timeline(const void* x, int N, int H, int W, int C, int ld, const void* w_packed, int Ipad, const float* bias,
                           int Cout, int ksize, int stride, void* out, int out_ld, int bn, int iters, void* dbg,
@@ -140,6 +145,10 @@ int rs_op_groupnorm(const void* x, int N, int H, int W, int C, int ld, const flo
                     const float* film, long long film_sN, int silu, void* y, int y_ld, float* sums_scratch,
                     void* stream);
 long long rs_op_groupnorm_scratch_floats(int N, int H, int W, int C);
+/* the apply half alone, on gstat[N][32][2] = (group mean, group rstd) delivered by a producer (rs_op_conv2d_stats) */
+int rs_op_groupnorm_apply(const void* x, int N, int H, int W, int C, int ld, const float* gamma, const float* beta,
+                          const float* film, long long film_sN, int silu, void* y, int y_ld, const float* gstat,
+                          void* stream);
 /* window attention core (reference models/swin_transformer.py:114-145,251-275); qkv [N,H,W,3*heads*32] */
 int rs_op_expand_relpos(const float* table_225xh, float* dense_hx64x64, int heads, void* stream);
 int rs_op_window_attention(const void* qkv, int N, int H, int W, int heads, int shift, const float* bias_dense,

@@ -65,15 +65,17 @@ _SIGNATURES = {
                                C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
     "rs_op_conv2d_stats": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int,
                                      C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,
-                                     C.POINTER(C.c_int32), _P]),
+                                     C.POINTER(C.c_int32), _P, _P, C.c_int, _P]),
     "rs_op_conv2d_splitk": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int,
                                       C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P,
-                                      C.POINTER(C.c_int32), _P]),
+                                      C.POINTER(C.c_int32), _P, _P, _P]),
     "rs_op_conv2d_timeline": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int,
                                         C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int32), _P, _P]),
     "rs_op_groupnorm": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_longlong, C.c_int,
                                   _P, C.c_int, _P, _P]),
     "rs_op_groupnorm_scratch_floats": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "rs_op_groupnorm_apply": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_longlong, C.c_int,
+                                        _P, C.c_int, _P, _P]),
     "rs_op_expand_relpos": (C.c_int, [_P, _P, C.c_int, _P]),
     "rs_op_window_attention": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "rs_op_mlp": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),

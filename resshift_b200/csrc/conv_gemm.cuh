@@ -17,6 +17,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "gn_stats.cuh"
 
 namespace rs {
 
@@ -75,11 +76,9 @@ struct ConvParams {
   int tma_res;
   int epi_bc;                        // staging block width in columns: 64 / 32 / 16 (swizzle 128B / 64B / 32B),
                                      // the largest that divides BN so a block never spills into the next channel tile
-  // fused GroupNorm statistics of the OUTPUT (per image, per 128-pixel tile slot, per channel: sum, sum of squares),
-  // written as deterministic partials [N][slots][cstride][2] for up to two consumers
-  float* gn_part[2];
-  int gn_cstride[2];
-  int gn_coff[2];
+  // fused GroupNorm statistics of the OUTPUT for up to two consumers (gn_stats.cuh): per image / 128-pixel tile slot /
+  // channel the pair (mean, M2) of the stored fp16 values; the last CTA to finish an image reduces its 32 groups
+  GnSink sink[2];
   int gn_slots;
   // persistent variant (conv_persist.cuh): CTAs (pairs) walk work units u = worker, worker + #workers, ...
   int persist;
@@ -335,19 +334,16 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
         }
         mbar_wait(res_bar, 0);
       }
-      const bool want_stats = p.gn_part[0] != nullptr;
+      const bool want_stats = p.sink[0].part != nullptr;
       for (int sub = 0; sub < p.msub; ++sub) {
         int tw, th, w0, h0, n0;
         tile_origin(sub, tw, th, w0, h0, n0);
-        const bool row_ok = (w0 + lw < p.Wout) && (h0 + lh < p.Hout) && (n0 + ln < p.Nimg);
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + sub * p.BN;
         uint8_t* sblk = smem + (size_t)sub * sub_bytes;
-        float* wsum = wsum_all + (size_t)sub * 4 * p.BN * 2;                           // [4 quads][BN][2]
         uint32_t vn[16];
         if (cpar * 16 < p.BN) tmem_ld16(trow + cpar * 16, vn);
         for (int c = cpar * 16; c < p.BN; c += 32) {
           tmem_ld_wait16(vn);
-          const int col = col0 + c;
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(vn[j]);
@@ -393,42 +389,6 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
             q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
           }
           *a0 = o0; *a1 = o1;
-          if (want_stats) {
-            // statistics of the values as stored (fp16-rounded), zero for rows / columns outside the tensor
-            float sv[16], sq[16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 x0 = __half22float2(q0[j]);
-              const float2 x1 = __half22float2(q1[j]);
-              sv[2 * j] = x0.x; sv[2 * j + 1] = x0.y; sv[8 + 2 * j] = x1.x; sv[8 + 2 * j + 1] = x1.y;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (!row_ok || col + j >= p.Cout) sv[j] = 0.f;
-              sq[j] = sv[j] * sv[j];
-            }
-            // transpose-reduce over the 32 rows of this warp: 16 shuffles per moment
-#pragma unroll
-            for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-              const bool upper = (lane & bit) != 0;
-#pragma unroll
-              for (int j = 0; j < half; ++j) {
-                const float send_s = upper ? sv[j] : sv[j + half];
-                const float keep_s = upper ? sv[j + half] : sv[j];
-                sv[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
-                const float send_q = upper ? sq[j] : sq[j + half];
-                const float keep_q = upper ? sq[j + half] : sq[j];
-                sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
-              }
-            }
-            sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
-            sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
-            if ((lane & 1) == 0) {
-              const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-              wsum[((size_t)quad * p.BN + c + cidx) * 2] = sv[0];
-              wsum[((size_t)quad * p.BN + c + cidx) * 2 + 1] = sq[0];
-            }
-          }
         }
       }
       fence_proxy_async_smem();
@@ -445,37 +405,23 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
         tma_store_commit();
       }
       if (want_stats) {
+        // column statistics of the staged (fp16-rounded) tile, read back from shared memory while the TMA store drains
+        float* wstat = wsum_all;                                     // [2 halves][BN][2]
+        int* s_flag = reinterpret_cast<int*>(wstat + 4 * p.BN);
         for (int sub = 0; sub < p.msub; ++sub) {
           int tw, th, w0, h0, n0;
           tile_origin(sub, tw, th, w0, h0, n0);
-          if (n0 >= p.Nimg) continue;                  // padding tile of an odd pair
-          const float* wsum = wsum_all + (size_t)sub * 4 * p.BN * 2;
+          staged_tile_column_stats(smem + (size_t)sub * sub_bytes, p.BN, bc, etid, wstat);
+          named_bar_sync(1, 32 * kConvEpiWarps);
+          const int ncols = min(p.BN, p.Cout - col0);
           const int slot = th * p.tiles_w + tw;
-          for (int cc = etid; cc < p.BN; cc += 32 * kConvEpiWarps) {
-            if (col0 + cc >= p.Cout) continue;
-            const float s0 = wsum[((size_t)0 * p.BN + cc) * 2], q0s = wsum[((size_t)0 * p.BN + cc) * 2 + 1];
-            const float s1 = wsum[((size_t)1 * p.BN + cc) * 2], q1s = wsum[((size_t)1 * p.BN + cc) * 2 + 1];
-            const float s2 = wsum[((size_t)2 * p.BN + cc) * 2], q2s = wsum[((size_t)2 * p.BN + cc) * 2 + 1];
-            const float s3 = wsum[((size_t)3 * p.BN + cc) * 2], q3s = wsum[((size_t)3 * p.BN + cc) * 2 + 1];
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-              float* part = p.gn_part[d];
-              if (!part) continue;
-              const size_t ch = (size_t)p.gn_coff[d] + col0 + cc;
-              if (p.bn == 1) {
-                float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
-                dst[0] = (s0 + s1) + (s2 + s3);
-                dst[1] = (q0s + q1s) + (q2s + q3s);
-              } else {   // two images per tile: rows 0..63 -> n0, rows 64..127 -> n0 + 1
-                float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
-                dst[0] = s0 + s1; dst[1] = q0s + q1s;
-                if (n0 + 1 < p.Nimg) {
-                  float* dst1 = part + (((size_t)(n0 + 1) * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
-                  dst1[0] = s2 + s3; dst1[1] = q2s + q3s;
-                }
-              }
-            }
-          }
+          if (n0 < p.Nimg)                                           // (else: padding tile of an odd pair)
+            write_tile_pairs(wstat, p.BN, ncols, col0, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kConvEpiWarps);
+          const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
+          const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
+          const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
+          const unsigned int ad[4] = {(unsigned)ncols, (unsigned)ncols, (unsigned)ncols, (unsigned)ncols};
+          gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kConvEpiWarps, 1, s_flag);
         }
       }
       if (etid == 0) tma_store_wait_read();
@@ -583,43 +529,32 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
           }
           *reinterpret_cast<uint4*>(s_out + (size_t)rr * cw + cu * 8) = o;                  // zeros outside the tensor
         }
-        if (p.gn_part[0] != nullptr) {
+        if (p.sink[0].part != nullptr) {
           named_bar_sync(1, 32 * kConvEpiWarps);
-          // column sums of the stored values over the two 64-row halves, rows in order
+          // (mean, M2) of the stored values per column over the two 64-row halves (pivot = first row, rows in order)
           for (int t = etid; t < 2 * cw; t += 32 * kConvEpiWarps) {
             const int half = t / cw, c = t - half * cw;
-            float sv = 0.f, qv = 0.f;
-            for (int rr = half * 64; rr < half * 64 + 64; ++rr) {
-              const float v = __half2float(s_out[(size_t)rr * cw + c]);
-              sv += v; qv += v * v;
+            const __half* col = s_out + (size_t)(half * 64) * cw + c;
+            const float pv = __half2float(col[0]);
+            float s1 = 0.f, s2 = 0.f;
+            for (int rr = 1; rr < 64; ++rr) {
+              const float d = __half2float(col[(size_t)rr * cw]) - pv;
+              s1 += d; s2 = fmaf(d, d, s2);
             }
-            s_col[(half * cw + c) * 2] = sv; s_col[(half * cw + c) * 2 + 1] = qv;
+            s_col[(half * cw + c) * 2] = pv + s1 * (1.0f / 64.0f);
+            s_col[(half * cw + c) * 2 + 1] = fmaxf(s2 - s1 * s1 * (1.0f / 64.0f), 0.f);
           }
           named_bar_sync(1, 32 * kConvEpiWarps);
-          if (n0 < p.Nimg) {
-            const int slot = th * p.tiles_w + tw;
-            for (int c = etid; c < cw; c += 32 * kConvEpiWarps) {
-              const int col = col0 + cbase + c;
-              if (col >= p.Cout) continue;
-              const float sl = s_col[c * 2], ql = s_col[c * 2 + 1], sh = s_col[(cw + c) * 2], qh = s_col[(cw + c) * 2 + 1];
-#pragma unroll
-              for (int dI = 0; dI < 2; ++dI) {
-                float* part = p.gn_part[dI];
-                if (!part) continue;
-                const size_t ch = (size_t)p.gn_coff[dI] + col;
-                float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[dI] + ch) * 2;
-                if (p.bn == 1) {
-                  dst[0] = sl + sh; dst[1] = ql + qh;
-                } else {   // two images per tile: rows 0..63 -> n0, rows 64..127 -> n0 + 1
-                  dst[0] = sl; dst[1] = ql;
-                  if (n0 + 1 < p.Nimg) {
-                    float* dst1 = part + (((size_t)(n0 + 1) * p.gn_slots + slot) * p.gn_cstride[dI] + ch) * 2;
-                    dst1[0] = sh; dst1[1] = qh;
-                  }
-                }
-              }
-            }
-          }
+          const int slot = th * p.tiles_w + tw;
+          const int ncols = max(0, min(cw, p.Cout - (col0 + cbase)));
+          if (n0 < p.Nimg)
+            write_tile_pairs(s_col, cw, ncols, col0 + cbase, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kConvEpiWarps);
+          int* s_flag = reinterpret_cast<int*>(s_col + 4 * cw);
+          const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
+          const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
+          const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
+          const unsigned int ad[4] = {(unsigned)ncols, (unsigned)ncols, (unsigned)ncols, (unsigned)ncols};
+          gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kConvEpiWarps, 1, s_flag);
         }
       }
     }

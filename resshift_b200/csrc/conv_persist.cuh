@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
     const int blk_bytes = kConvBM * bc * 2;
     const int bshift = (bc == 64) ? 6 : (bc == 32 ? 5 : 4);
     const int swz = (bc == 64) ? (r & 7) : (bc == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
-    const bool want_stats = p.gn_part[0] != nullptr;
+    const bool want_stats = p.sink[0].part != nullptr;
     const uint32_t lead_acc_empty = kCG == 2 ? mapa_u32(smem_u32(acc_empty), 0) : smem_u32(acc_empty);
     int i = 0;
     auto load_bias = [&](int u, float* dst) {
@@ -187,7 +187,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
       int n_tile, tw, th, w0, h0, n0;
       unit_tile(u, n_tile, tw, th, w0, h0, n0);
       const int col0 = n_tile * p.BN;
-      const bool row_ok = (w0 + lw < p.Wout) && (h0 + lh < p.Hout) && (n0 + ln < p.Nimg);
       uint8_t* s_stage = s_stage0 + (size_t)b * stage_sz;
       const float* s_bias = s_bias0 + (size_t)b * p.BN;
       // this staging buffer was last used by tile i-2: its TMA store has read it (tile i-1's may still be draining);
@@ -209,7 +208,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
       if (cpar * 16 < p.BN) tmem_ld16(trow + cpar * 16, vn);
       for (int c = cpar * 16; c < p.BN; c += 32) {
         tmem_ld_wait16(vn);
-        const int col = col0 + c;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(vn[j]);
@@ -254,41 +252,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
           q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
         }
         *a0 = o0; *a1 = o1;
-        if (want_stats) {
-          // statistics of the values as stored (fp16-rounded), zero for rows / columns outside the tensor
-          float sv[16], sq[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 x0 = __half22float2(q0[j]);
-            const float2 x1 = __half22float2(q1[j]);
-            sv[2 * j] = x0.x; sv[2 * j + 1] = x0.y; sv[8 + 2 * j] = x1.x; sv[8 + 2 * j + 1] = x1.y;
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (!row_ok || col + j >= p.Cout) sv[j] = 0.f;
-            sq[j] = sv[j] * sv[j];
-          }
-#pragma unroll
-          for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-            const bool upper = (lane & bit) != 0;
-#pragma unroll
-            for (int j = 0; j < half; ++j) {
-              const float send_s = upper ? sv[j] : sv[j + half];
-              const float keep_s = upper ? sv[j + half] : sv[j];
-              sv[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
-              const float send_q = upper ? sq[j] : sq[j + half];
-              const float keep_q = upper ? sq[j + half] : sq[j];
-              sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
-            }
-          }
-          sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
-          sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
-          if ((lane & 1) == 0) {
-            const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            wsum[((size_t)quad * p.BN + c + cidx) * 2] = sv[0];
-            wsum[((size_t)quad * p.BN + c + cidx) * 2 + 1] = sq[0];
-          }
-        }
       }
       // this warp has read its share of the accumulator: hand the buffer back to the MMA issuer (tile i + 2)
       tc_fence_before();
@@ -303,32 +266,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
           if (col0 + bq * bc < p.Cout) tma_store_4d(&p.tmOut, s_stage + (size_t)bq * blk_bytes, col0 + bq * bc, w0, h0, n0);
         tma_store_commit();
       }
-      if (want_stats && n0 < p.Nimg) {
+      if (want_stats) {
+        // column statistics of the staged (fp16-rounded) tile, read back from shared memory while its TMA store drains
+        float* wstat = wsum;                                         // [2 halves][BN][2]
+        int* s_flag = reinterpret_cast<int*>(wstat + 4 * p.BN);
+        staged_tile_column_stats(s_stage, p.BN, bc, etid, wstat);
+        named_bar_sync(1, 32 * kConvEpiWarps);
+        const int ncols = min(p.BN, p.Cout - col0);
         const int slot = th * p.tiles_w + tw;
-        for (int cc = etid; cc < p.BN; cc += 32 * kConvEpiWarps) {
-          if (col0 + cc >= p.Cout) continue;
-          const float s0 = wsum[((size_t)0 * p.BN + cc) * 2], q0s = wsum[((size_t)0 * p.BN + cc) * 2 + 1];
-          const float s1 = wsum[((size_t)1 * p.BN + cc) * 2], q1s = wsum[((size_t)1 * p.BN + cc) * 2 + 1];
-          const float s2 = wsum[((size_t)2 * p.BN + cc) * 2], q2s = wsum[((size_t)2 * p.BN + cc) * 2 + 1];
-          const float s3 = wsum[((size_t)3 * p.BN + cc) * 2], q3s = wsum[((size_t)3 * p.BN + cc) * 2 + 1];
-#pragma unroll
-          for (int dI = 0; dI < 2; ++dI) {
-            float* part = p.gn_part[dI];
-            if (!part) continue;
-            const size_t ch = (size_t)p.gn_coff[dI] + col0 + cc;
-            float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[dI] + ch) * 2;
-            if (p.bn == 1) {
-              dst[0] = (s0 + s1) + (s2 + s3);
-              dst[1] = (q0s + q1s) + (q2s + q3s);
-            } else {   // two images per tile: rows 0..63 -> n0, rows 64..127 -> n0 + 1
-              dst[0] = s0 + s1; dst[1] = q0s + q1s;
-              if (n0 + 1 < p.Nimg) {
-                float* dst1 = part + (((size_t)(n0 + 1) * p.gn_slots + slot) * p.gn_cstride[dI] + ch) * 2;
-                dst1[0] = s2 + s3; dst1[1] = q2s + q3s;
-              }
-            }
-          }
-        }
+        if (n0 < p.Nimg)                                             // (else: padding tile of an odd pair)
+          write_tile_pairs(wstat, p.BN, ncols, col0, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kConvEpiWarps);
+        const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
+        const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
+        const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
+        const unsigned int ad[4] = {(unsigned)ncols, (unsigned)ncols, (unsigned)ncols, (unsigned)ncols};
+        gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kConvEpiWarps, 1, s_flag);
       }
     }
     if (etid == 0) tma_store_wait_read();

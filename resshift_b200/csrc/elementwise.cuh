@@ -3,6 +3,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "gn_stats.cuh"
 
 namespace rs {
 
@@ -21,12 +22,14 @@ struct PackInputParams {
   const __half* lq_nhwc; int lq_ld;   // [N*H*W, Cl] fp16 or nullptr
   __half* out; int Cpad;              // [N*H*W, Cpad]
   int N, HW;
+  unsigned int* zero_ptr; int zero_n; // GroupNorm arrival counters of the forward that follows (gn_stats.cuh): reset here
 };
 
 __global__ void pack_input_kernel(const PackInputParams p) {
   pdl_trigger();
   pdl_wait();
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix < p.zero_n) p.zero_ptr[pix] = 0u;
   const long long total = (long long)p.N * p.HW;
   if (pix >= total) return;
   const int n = (int)(pix / p.HW);
@@ -151,11 +154,13 @@ struct PSampleParams {
   int t;                  // schedule index of THIS step (T-1 .. 0)
   int N, C, HW;
   __half* next_in; int next_cpad;     // optional: [N*HW, next_cpad]; channels [0, C) are written here
+  unsigned int* zero_ptr; int zero_n; // GroupNorm arrival counters of the NEXT denoiser forward: reset here
 };
 __global__ void p_sample_kernel(const PSampleParams p) {
   pdl_trigger();
   pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.zero_n) p.zero_ptr[i] = 0u;
   const long long total = (long long)p.N * p.C * p.HW;
   if (i >= total) return;
   const float c1 = p.coef1[p.t], c2 = p.coef2[p.t];
@@ -194,13 +199,13 @@ struct SplitKReduceParams {
   int act;
   int rows_per_slot, slots;
   int cols_per_cta;         // multiple of 8; grid.z = ceil(C / cols_per_cta)
-  float* gn_part[2]; int gn_cstride[2]; int gn_coff[2];
+  GnSink sink[2];           // fused GroupNorm statistics of the result (gn_stats.cuh)
 };
 
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitKReduceParams p) {
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constant__ SplitKReduceParams p) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float s_red[];       // [lanes][cols_per_cta][2]
+  extern __shared__ float s_red[];       // [lanes][cols_per_cta][3] = (rows, mean, M2) per row-lane and column; + 4 flags
   const int c_begin = blockIdx.z * p.cols_per_cta;
   const int ccols = min(p.cols_per_cta, p.C - c_begin);
   const int vecs = ccols >> 3;
@@ -208,11 +213,13 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitKReducePa
   const int n = blockIdx.y, slot = blockIdx.x;
   const int vec = threadIdx.x % vecs, rl = threadIdx.x / vecs;
   const long long npix = (long long)p.N * p.HW;
-  const bool want_stats = p.gn_part[0] != nullptr;
+  const bool want_stats = p.sink[0].part != nullptr;
   if (rl < lanes) {
-    float ssum[8], qsum[8];
+    // statistics of the stored values around a pivot (this thread's first row): no cancellation for |mean| >> std
+    float pv[8], s1[8], s2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ssum[j] = 0.f; qsum[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { pv[j] = 0.f; s1[j] = 0.f; s2[j] = 0.f; }
+    int cnt = 0;
     const int r0 = slot * p.rows_per_slot, r1 = min(r0 + p.rows_per_slot, p.HW);
     const int c = c_begin + vec * 8;
     float bs[8];
@@ -247,31 +254,57 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitKReducePa
       for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
       *reinterpret_cast<uint4*>(p.out + n * p.out_sN + (long long)r * p.out_ld + c) = o;
       if (want_stats) {
+        float st[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(oh[j]);
-          ssum[2 * j] += f.x; qsum[2 * j] += f.x * f.x;
-          ssum[2 * j + 1] += f.y; qsum[2 * j + 1] += f.y * f.y;
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(oh[j]); st[2 * j] = f.x; st[2 * j + 1] = f.y; }
+        if (cnt == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pv[j] = st[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float d = st[j] - pv[j]; s1[j] += d; s2[j] = fmaf(d, d, s2[j]); }
         }
+        ++cnt;
       }
     }
     if (want_stats) {
-      float* dst = s_red + ((size_t)rl * ccols + vec * 8) * 2;
+      float* dst = s_red + ((size_t)rl * ccols + vec * 8) * 3;
+      const float inv = cnt ? 1.0f / (float)cnt : 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { dst[2 * j] = ssum[j]; dst[2 * j + 1] = qsum[j]; }
+      for (int j = 0; j < 8; ++j) {
+        dst[3 * j] = (float)cnt;
+        dst[3 * j + 1] = pv[j] + s1[j] * inv;
+        dst[3 * j + 2] = fmaxf(s2[j] - s1[j] * s1[j] * inv, 0.f);
+      }
     }
   }
   if (!want_stats) return;
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * ccols; i += blockDim.x) {
-    float acc = 0.f;
-    for (int l = 0; l < lanes; ++l) acc += s_red[(size_t)l * ccols * 2 + i];
-    const int ch = c_begin + (i >> 1), m = i & 1;
+  // merge the row-lanes of each column in lane order (Chan et al.), then deliver the slot's pair to the sinks
+  for (int i = threadIdx.x; i < ccols; i += blockDim.x) {
+    float cn = 0.f, mean = 0.f, m2 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      const float* e = s_red + ((size_t)l * ccols + i) * 3;
+      const float nb = e[0];
+      if (nb == 0.f) continue;
+      const float tot = cn + nb, d = e[1] - mean;
+      mean += d * (nb / tot);
+      m2 += e[2] + d * d * (cn * nb / tot);
+      cn = tot;
+    }
+    const int ch = c_begin + i;
 #pragma unroll
     for (int d = 0; d < 2; ++d)
-      if (p.gn_part[d])
-        p.gn_part[d][(((size_t)n * p.slots + slot) * p.gn_cstride[d] + p.gn_coff[d] + ch) * 2 + m] = acc;
+      if (p.sink[d].part) {
+        float* dst = p.sink[d].part + (((size_t)n * p.slots + slot) * p.sink[d].cstride + p.sink[d].coff + ch) * 2;
+        dst[0] = mean; dst[1] = m2;
+      }
   }
+  int* s_flag = reinterpret_cast<int*>(s_red + (size_t)lanes * ccols * 3);
+  const GnSink* const sk[2] = {&p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr};
+  const int im[2] = {n, n};
+  const unsigned int ad[2] = {(unsigned)ccols, (unsigned)ccols};
+  gn_arrive<2>(sk, im, ad, p.slots, (float)p.rows_per_slot, threadIdx.x, blockDim.x, 1, s_flag);
 }
 
 // ------------------------------------------------------------------------------------------------

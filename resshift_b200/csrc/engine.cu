@@ -275,7 +275,8 @@ struct Op {
   MlpDesc mlp;
   std::string w2_name, b2_name;
   std::string w_name, b_name, g_name;   // parameter names resolved at bind
-  size_t stats_off = 0;                 // GroupNorm: offset of its partial-sum buffer inside the stats region
+  size_t stats_off = 0;                 // GroupNorm: offset of its (mean, M2) pair buffer inside the stats region
+  int gn_index = -1;                    // GroupNorm: index of its [N][32][2] group statistics / [N] arrival counters
   bool to_f32 = false;                  // conv: writes the fp32 NCHW model output
   int split_tens = -1;                  // conv: workspace tensor holding split-K partial sums (or -1)
   struct StatDst { int list; int op; int coff; };
@@ -293,6 +294,8 @@ struct rs_plan {
   // fixed regions (byte offsets in the workspace)
   size_t off_emb_sin = 0, off_emb_mid = 0, off_emb_vec = 0, off_film = 0, off_tsteps = 0, off_tables = 0;
   size_t off_stats = 0, stats_bytes = 0, off_state = 0, off_temps = 0, temps_bytes = 0;
+  size_t off_gstat = 0, off_counters = 0;   // per GroupNorm: [N][32][2] floats (mean, rstd); [N] arrival counters
+  int n_gn = 0;
   size_t workspace_bytes = 0;
   int max_rows = 0;          // rows of the FiLM table (max(B, 64) so a sampler with T <= 64 fits)
   uint8_t* ws = nullptr;
@@ -334,13 +337,15 @@ struct Builder {
   rs_engine& E;
   std::vector<Op>* cur;
   size_t stats_off = 0;
+  int n_gn = 0;
   struct Writer { long long off; int C; int list; int op; };
   std::map<int, std::vector<Writer>> writers;      // tensor id -> latest conv writers by channel range
   const bool fuse_mlp = env_int("RS_MLP_FUSE", 1) && !env_is("RS_CONV_IMPL", "simt");
-  // norm2 applied inside the fused MLP kernel: implemented and bit-identical, but OFF by default — every (non-persistent)
-  // MLP CTA re-derives the affine from the partial sums before its first MMA, which costs more than the gn_apply launch it
-  // saves (64x64: +21 us vs -16 us, profiles/r1_s32_*); needs a persistent MLP kernel or a finalize pass to pay off
-  const bool fuse_mlp_norm = env_int("RS_MLP_NORM_FUSE", 0) != 0;
+  // norm2 applied inside the fused MLP kernel (bit-identical to the separate pass).  Round 1 kept it off because every MLP
+  // CTA re-derived the affine from slots x C partial sums; with the group statistics finalised by the producer's last CTA
+  // (gn_stats.cuh) the preamble is one 256-byte read per image, so it is ON: one launch and one activation round trip
+  // less per Swin block (RS_MLP_NORM_FUSE=0 restores the separate gn_apply launch)
+  const bool fuse_mlp_norm = env_int("RS_MLP_NORM_FUSE", 1) != 0;
   const bool fuse_stats = env_int("RS_GN_FUSE", 1) && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt");
   Builder(rs_plan& p) : P(p), E(*p.e), cur(&p.ops) {}
   int list_id() const { return cur == &P.fe_ops ? 0 : 1; }
@@ -399,6 +404,7 @@ struct Builder {
     op.gn.fused = !prod.empty();
     op.gn.slots = op.gn.fused ? tile_slots : chunks;
     op.stats_off = stats_off;
+    op.gn_index = n_gn++;
     stats_off += align_up((size_t)in.N * op.gn.slots * in.C * 2 * sizeof(float), 256);
     const int i = opi();
     P.touch(in, i); P.touch(out, i);
@@ -445,6 +451,7 @@ struct Builder {
       op.g_name = norm_name;
       op.gn.in = in; op.gn.fused = true; op.gn.slots = conv_tile_slots(in.H, in.W);
       op.stats_off = stats_off;
+      op.gn_index = n_gn++;
       stats_off += align_up((size_t)in.N * op.gn.slots * in.C * 2 * sizeof(float), 256);
     }
     const int i = opi();
@@ -650,6 +657,9 @@ int build_plan(rs_plan& P) {
   P.off_film = region((size_t)P.max_rows * E.film_rows * sizeof(float));
   P.stats_bytes = b.stats_off;
   P.off_stats = region(P.stats_bytes);
+  P.n_gn = b.n_gn;
+  P.off_gstat = region((size_t)P.n_gn * B * 32 * 2 * sizeof(float));
+  P.off_counters = region((size_t)P.n_gn * B * sizeof(unsigned int));
   // sampler state: x_t (fp32), model output / pred_xstart (fp32)
   const size_t lat = (size_t)B * std::max(c.in_channels, c.out_channels) * P.H * P.W * sizeof(float);
   P.off_state = region(2 * align_up(lat, 256));
@@ -688,18 +698,25 @@ void resolve(rs_plan& P, View& v) {
   if (v.tens >= 0) v.ptr = reinterpret_cast<__half*>(P.ws + P.tensors[v.tens].off) + v.off;
 }
 
+// statistics destination of a producer: the consuming GroupNorm's pair buffer / group statistics / arrival counters
+GnSink make_sink(rs_plan& P, const Op& g, int coff) {
+  GnSink s{};
+  s.part = reinterpret_cast<float*>(P.ws + P.off_stats + g.stats_off);
+  s.gstat = reinterpret_cast<float*>(P.ws + P.off_gstat) + (size_t)g.gn_index * P.B * 64;
+  s.counter = reinterpret_cast<unsigned int*>(P.ws + P.off_counters) + (size_t)g.gn_index * P.B;
+  s.cstride = g.gn.in.C; s.coff = coff; s.expected = (unsigned)(g.gn.slots * g.gn.in.C); s.eps = g.gn.eps;
+  return s;
+}
+
 int bind_ops(rs_plan& P, std::vector<Op>& ops) {
   rs_engine& E = *P.e;
   for (Op& op : ops) {
     if (op.kind == OP_CONV) {
       for (int i = 0; i < 2; ++i) {
-        op.conv.gn_part[i] = nullptr;
+        op.conv.sink[i] = GnSink{};
         if (i < (int)op.stat_dst.size()) {
           const Op::StatDst& sd = op.stat_dst[i];
-          const Op& g = (sd.list == 0 ? P.fe_ops : P.ops)[sd.op];
-          op.conv.gn_part[i] = reinterpret_cast<float*>(P.ws + P.off_stats + g.stats_off);
-          op.conv.gn_cstride[i] = g.gn.in.C;
-          op.conv.gn_coff[i] = sd.coff;
+          op.conv.sink[i] = make_sink(P, (sd.list == 0 ? P.fe_ops : P.ops)[sd.op], sd.coff);
         }
       }
       ConvDesc& d = op.conv;
@@ -718,7 +735,10 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       resolve(P, op.gn.in); resolve(P, op.gn.out);
       op.gn.gamma = E.at<float>(op.g_name + ".weight"); op.gn.beta = E.at<float>(op.g_name + ".bias");
       RS_CHECK(op.gn.gamma && op.gn.beta, "missing GroupNorm parameters " + op.g_name);
-      op.gn.part = reinterpret_cast<float*>(P.ws + P.off_stats + op.stats_off);
+      {
+        const GnSink sk = make_sink(P, op, 0);
+        op.gn.part = sk.part; op.gn.gstat = sk.gstat; op.gn.counter = sk.counter;
+      }
       P.launches += op.gn.fused ? 1 : 2;
     } else if (op.kind == OP_MLP) {
       MlpDesc& m = op.mlp;
@@ -729,19 +749,15 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       const Param* w1p = E.find(op.w_name); const Param* w2p = E.find(op.w2_name);
       RS_CHECK(w1p->ipad == m.E && w2p->ipad == m.Hd, "MLP weight padding");
       if (!op.g_name.empty()) {
-        m.gn_in_part = reinterpret_cast<const float*>(P.ws + P.off_stats + op.stats_off);
-        m.gn_in_slots = op.gn.slots;
+        m.gn_in_gstat = make_sink(P, op, 0).gstat;
         m.gn_in_gamma = E.at<float>(op.g_name + ".weight"); m.gn_in_beta = E.at<float>(op.g_name + ".bias");
         RS_CHECK(m.gn_in_gamma && m.gn_in_beta, "missing GroupNorm parameters " + op.g_name);
       }
       for (int i = 0; i < 2; ++i) {
-        m.gn_part[i] = nullptr;
+        m.sink[i] = GnSink{};
         if (i < (int)op.stat_dst.size()) {
           const Op::StatDst& sd = op.stat_dst[i];
-          const Op& g = (sd.list == 0 ? P.fe_ops : P.ops)[sd.op];
-          m.gn_part[i] = reinterpret_cast<float*>(P.ws + P.off_stats + g.stats_off);
-          m.gn_cstride[i] = g.gn.in.C;
-          m.gn_coff[i] = sd.coff;
+          m.sink[i] = make_sink(P, (sd.list == 0 ? P.fe_ops : P.ops)[sd.op], sd.coff);
         }
       }
       int rc = mlp_finalize(m); if (rc) return rc;
@@ -850,6 +866,7 @@ int pack_lq_and_input(rs_plan& P, const float* x, const float* lq, const float* 
   PackInputParams pp{};
   pp.x = x; pp.Cx = c.in_channels; pp.scale_tab = scale_tab; pp.scale_idx = scale_idx;
   pp.out = P.xin.ptr; pp.Cpad = P.cin_pad; pp.N = P.B; pp.HW = P.H * P.W;
+  pp.zero_ptr = reinterpret_cast<unsigned int*>(P.ws + P.off_counters); pp.zero_n = P.n_gn * P.B;
   if (E.fe_stages() > 0) {
     RS_CHECK(!c.cond_mask || mask != nullptr, "this model is mask-conditioned: mask must be given");
     PackImageParams ip{lq, 3, c.cond_mask ? mask : nullptr, c.cond_mask ? 1 : 0, P.fe_in.ptr, P.fe_cpad, P.B, P.lqH * P.lqW};
@@ -1121,6 +1138,7 @@ int sampler_enqueue(rs_sampler& S, const float* z_y, const float* noises, const 
     pp.coef1 = coef1; pp.coef2 = coef2; pp.stdv = stdv; pp.in_scale = in_scale; pp.t = t;
     pp.N = P.B; pp.C = c.in_channels; pp.HW = P.H * P.W;
     pp.next_in = P.xin.ptr; pp.next_cpad = P.cin_pad;
+    pp.zero_ptr = reinterpret_cast<unsigned int*>(P.ws + P.off_counters); pp.zero_n = P.n_gn * P.B;
     if (S.tap_pred) RS_CUDA_OK(cudaMemcpyAsync(S.tap_pred + (long long)k * numel, P.out_f32, numel * 4, cudaMemcpyDeviceToDevice, st));
     (void)launch_k(p_sample_kernel, dim3((unsigned)((numel + 255) / 256)), dim3(256), (size_t)(0), st, pp);
     if (S.tap_sample) RS_CUDA_OK(cudaMemcpyAsync(S.tap_sample + (long long)k * numel, pp.x_next, numel * 4, cudaMemcpyDeviceToDevice, st));

@@ -146,10 +146,9 @@ struct ConvDesc {
   bool allow_split = false;
   SplitKReduceParams red;         // filled by finalize() when S > 1
   int red_grid_x = 0, red_grid_z = 1; size_t red_smem = 0;
-  // fused GroupNorm partial statistics of the output (up to two consumers)
-  float* gn_part[2] = {nullptr, nullptr};
-  int gn_cstride[2] = {0, 0};
-  int gn_coff[2] = {0, 0};
+  // fused GroupNorm statistics of the output (up to two consumers; gn_stats.cuh).  `expected` is filled by finalize()
+  // (slots * cstride) unless the caller set it (a statistics buffer only partly covered by this producer: unit tests)
+  GnSink sink[2] = {};
   // filled by finalize()
   ConvParams prm;
   ConvSimtSrc simt;
@@ -231,7 +230,7 @@ inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn
             if (mode == 1 && (S != 2 || !allow_cluster_split || cg != 2 || occ != 1 || (cand / S) % 8 != 0)) continue;
             if (mode == 1 && f_mode && std::strcmp(f_mode, "global") == 0) continue;
             if (mode == 0 && S > 1 && f_mode && std::strcmp(f_mode, "cluster") == 0) continue;
-            if (mode == 1 && (size_t)kConvBM * (cand * 4 + 16) + (size_t)kConvBM * (cand / S) * 2 + (size_t)4 * (cand / S) * 4 > (size_t)st * sbytes) continue;
+            if (mode == 1 && (size_t)kConvBM * (cand * 4 + 16) + (size_t)kConvBM * (cand / S) * 2 + (size_t)4 * (cand / S) * 4 + 16 > (size_t)st * sbytes) continue;
             if (S > 1 && ((mode == 0 && !allow_split) || ms != 1 || num_kb / S < 6)) continue;
             if (f_split && (allow_split || allow_cluster_split) && ms == 1 && num_kb / f_split >= 6 && S != f_split) continue;
             const double waves = std::ceil((double)units * S / slots);
@@ -388,23 +387,28 @@ inline int conv_finalize(ConvDesc& d) {
     }
   }
   p.gn_slots = p.tiles_w * p.tiles_h;
-  RS_CHECK(!(d.gn_part[0] || d.gn_part[1]) || p.bn <= 2, "fused GroupNorm statistics need tiles of at most two images");
-  for (int i = 0; i < 2; ++i) {
-    p.gn_part[i] = p.tma_out ? d.gn_part[i] : nullptr;
-    p.gn_cstride[i] = d.gn_cstride[i]; p.gn_coff[i] = d.gn_coff[i];
-  }
-  if (p.gn_part[0] == nullptr && p.gn_part[1] != nullptr) {
-    p.gn_part[0] = p.gn_part[1]; p.gn_cstride[0] = p.gn_cstride[1]; p.gn_coff[0] = p.gn_coff[1]; p.gn_part[1] = nullptr;
+  RS_CHECK(!(d.sink[0].part || d.sink[1].part) || p.bn <= 2, "fused GroupNorm statistics need tiles of at most two images");
+  auto fill_sinks = [&](GnSink* dst) {
+    int k = 0;
+    for (int i = 0; i < 2; ++i) {
+      dst[i] = GnSink{};
+      if (!d.sink[i].part) continue;
+      dst[k] = d.sink[i];
+      if (dst[k].expected == 0) dst[k].expected = (unsigned)(p.gn_slots * dst[k].cstride);
+      if (dst[k].eps == 0.f) dst[k].eps = 1e-5f;
+      ++k;
+    }
+  };
+  {
+    GnSink none[2] = {};
+    if (p.tma_out) fill_sinks(p.sink); else { p.sink[0] = none[0]; p.sink[1] = none[1]; }
   }
   if (p.splitk > 1 && p.splitk_cluster) {
     // cluster split-K: the conv kernel finishes the layer itself (DSMEM reduce + direct epilogue), statistics included
-    for (int i = 0; i < 2; ++i) { p.gn_part[i] = d.gn_part[i]; }
-    if (p.gn_part[0] == nullptr && p.gn_part[1] != nullptr) {
-      p.gn_part[0] = p.gn_part[1]; p.gn_cstride[0] = p.gn_cstride[1]; p.gn_coff[0] = p.gn_coff[1]; p.gn_part[1] = nullptr;
-    }
+    fill_sinks(p.sink);
     RS_CHECK(cg == 2 && d.Cout % 8 == 0 && (BN / p.splitk) % 8 == 0, "cluster split-K configuration");
   } else if (p.splitk > 1) {
-    // the conv kernel only produces fp32 partial sums; bias / activation / residual / fp16 store / GroupNorm partials
+    // the conv kernel only produces fp32 partial sums; bias / activation / residual / fp16 store / GroupNorm statistics
     // happen in the reduce kernel, one CTA per (128-pixel slot, image)
     SplitKReduceParams& r = d.red;
     std::memset(&r, 0, sizeof(r));
@@ -413,12 +417,9 @@ inline int conv_finalize(ConvDesc& d) {
     if (d.has_res) { r.residual = d.res.ptr; r.res_sN = d.res.sN(); r.res_ld = d.res.ld; }
     r.out = d.out.ptr; r.out_sN = d.out.sN(); r.out_ld = d.out.ld;
     r.rows_per_slot = p.bw * p.bh; r.slots = p.tiles_w * p.tiles_h;
-    for (int i = 0; i < 2; ++i) { r.gn_part[i] = d.gn_part[i]; r.gn_cstride[i] = d.gn_cstride[i]; r.gn_coff[i] = d.gn_coff[i]; }
-    if (r.gn_part[0] == nullptr && r.gn_part[1] != nullptr) {
-      r.gn_part[0] = r.gn_part[1]; r.gn_cstride[0] = r.gn_cstride[1]; r.gn_coff[0] = r.gn_coff[1]; r.gn_part[1] = nullptr;
-    }
+    fill_sinks(r.sink);
     RS_CHECK(d.Cout % 8 == 0 && d.Cout <= 2048, "split-K reduce needs Cout % 8 == 0");
-    p.bias = nullptr; p.residual = nullptr; p.act = ACT_NONE; p.gn_part[0] = p.gn_part[1] = nullptr;
+    p.bias = nullptr; p.residual = nullptr; p.act = ACT_NONE; p.sink[0] = GnSink{}; p.sink[1] = GnSink{};
     d.red_grid_x = r.slots;
     // column blocks so that the reduce kernel fills the machine even with one slot per image
     int cpc = d.Cout;
@@ -426,7 +427,7 @@ inline int conv_finalize(ConvDesc& d) {
     r.cols_per_cta = cpc;
     d.red_grid_z = (d.Cout + cpc - 1) / cpc;
     const int lanes = 256 / std::max(1, cpc / 8);
-    d.red_smem = (size_t)std::max(1, lanes) * cpc * 2 * sizeof(float);
+    d.red_smem = (size_t)std::max(1, lanes) * cpc * 3 * sizeof(float) + 16;
   }
   // tensor maps + SIMT mirrors
   ConvSimtSrc& s = d.simt;
@@ -503,16 +504,20 @@ struct GnDesc {
   const float* film = nullptr; long long film_sN = 0;   // resolved per launch for FiLM layers
   int film_off = -1;      // offset of this layer's [2C] slice inside an embedding row, or -1
   int silu = 0;
-  float* part = nullptr;  // [N][slots][C][2]
+  float* part = nullptr;  // [N][slots][C][2] (mean, M2) pairs
+  float* gstat = nullptr; // [N][32][2] (mean, rstd), finalised by the last producer CTA of each image
+  unsigned int* counter = nullptr;   // [N]
+  float eps = 1e-5f;
   int slots = 0;
-  bool fused = false;     // statistics already written by the producing conv kernels
+  bool fused = false;     // statistics already delivered by the producing kernels' epilogues
 };
 
 inline void gn_chunks(int HW, int N, int* chunks, int* rows) {
-  // enough CTAs to fill the machine, at least 32 rows each
+  // enough CTAs to fill the machine, at least 32 rows each, and every chunk with the SAME number of rows (the
+  // statistics combine assumes equal counts per slot): the largest divisor of HW not above the target
   int c = std::max(1, std::min((HW + 31) / 32, (148 * 4 + N - 1) / N));
-  int r = (HW + c - 1) / c;
-  *chunks = (HW + r - 1) / r; *rows = r;
+  while (c > 1 && HW % c != 0) --c;
+  *chunks = c; *rows = HW / c;
 }
 
 inline int gn_launch(const GnDesc& g, cudaStream_t st) {
@@ -522,11 +527,17 @@ inline int gn_launch(const GnDesc& g, cudaStream_t st) {
   int chunks, rows;
   gn_chunks(HW, N, &chunks, &rows);
   int slots = g.slots;
+  RS_CHECK(g.gstat != nullptr, "GroupNorm needs the per-image group statistics buffer");
   if (!g.fused) {
     slots = chunks;
     const int lanes = 256 / (C / 8);
-    GnStatsParams sp{g.in.ptr, g.in.sN(), g.in.ld, C, HW, N, g.part, slots, rows};
-    (void)launch_k(gn_stats_kernel, dim3(chunks, N), dim3(256), (size_t)lanes * C * 2 * sizeof(float), st, sp);
+    RS_CHECK(g.part != nullptr && g.counter != nullptr, "GroupNorm statistics buffers");
+    GnStatsParams sp{};
+    sp.x = g.in.ptr; sp.sN = g.in.sN(); sp.ld = g.in.ld; sp.C = C; sp.HW = HW; sp.N = N;
+    sp.sink.part = g.part; sp.sink.gstat = g.gstat; sp.sink.counter = g.counter; sp.sink.cstride = C; sp.sink.coff = 0;
+    sp.sink.expected = (unsigned)(slots * C); sp.sink.eps = g.eps;
+    sp.slots = slots; sp.rows_per_slot = rows;
+    (void)launch_k(gn_stats_kernel, dim3(chunks, N), dim3(256), (size_t)lanes * C * 3 * sizeof(float) + 16, st, sp);
     RS_CUDA_OK(cudaGetLastError());
   }
   // apply: ~4 CTAs per SM in total, all resident at once (each CTA re-derives the per-channel affine from the
@@ -543,8 +554,9 @@ inline int gn_launch(const GnDesc& g, cudaStream_t st) {
     for (int cs = 2; actas * N * csplit < 222 && cs <= C / unit; ++cs)
       if (C % cs == 0 && (C / cs) % unit == 0) csplit = cs;
   }
-  GnApplyParams ap{g.in.ptr, g.in.sN(), g.in.ld, g.out.ptr, g.out.sN(), g.out.ld, C, HW, N, g.part, slots,
-                   g.gamma, g.beta, g.film, g.film_sN, g.silu, arows, 1e-5f, C / csplit};
+  GnApplyParams ap{g.in.ptr, g.in.sN(), g.in.ld, g.out.ptr, g.out.sN(), g.out.ld, C, HW, N, g.gstat,
+                   g.gamma, g.beta, g.film, g.film_sN, g.silu, arows, C / csplit};
+  (void)slots;
   (void)launch_k(gn_apply_kernel, dim3(actas, N, csplit), dim3(256), (size_t)(4 * (C / csplit) + 64) * sizeof(float), st, ap);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
@@ -557,12 +569,10 @@ struct MlpDesc {
   const __half* w1 = nullptr; const float* b1 = nullptr;    // fc1: [Hd][E] fp16
   const __half* w2 = nullptr; const float* b2 = nullptr;    // fc2: [E][Hd] fp16
   int E = 0, Hd = 0;
-  float* gn_part[2] = {nullptr, nullptr};
-  int gn_cstride[2] = {0, 0};
-  int gn_coff[2] = {0, 0};
+  GnSink sink[2] = {};
   long long* dbg = nullptr;
   // optional fused input GroupNorm (plain affine): `in` is then the un-normalised tensor
-  const float* gn_in_part = nullptr; int gn_in_slots = 0;
+  const float* gn_in_gstat = nullptr;
   const float* gn_in_gamma = nullptr; const float* gn_in_beta = nullptr;
   MlpParams prm;
   int grid = 0; size_t smem = 0;
@@ -627,14 +637,19 @@ inline int mlp_finalize(MlpDesc& d) {
     if (rc) return rc;
   }
   p.dbg = d.dbg;
-  p.gn_in_part = d.gn_in_part; p.gn_in_slots = d.gn_in_slots; p.gn_in_gamma = d.gn_in_gamma; p.gn_in_beta = d.gn_in_beta;
-  p.gn_in_eps = 1e-5f;
-  RS_CHECK(!d.gn_in_part || (d.gn_in_gamma && d.gn_in_beta && d.Hd >= 4 * d.E && d.E % 32 == 0 && d.gn_in_slots == p.tiles_w * p.tiles_h),
-           "fused MLP: input GroupNorm arguments");
+  p.gn_in_gstat = d.gn_in_gstat; p.gn_in_gamma = d.gn_in_gamma; p.gn_in_beta = d.gn_in_beta;
+  RS_CHECK(!d.gn_in_gstat || (d.gn_in_gamma && d.gn_in_beta && d.Hd >= 4 * d.E && d.E % 32 == 0), "fused MLP: input GroupNorm arguments");
   p.gn_slots = p.tiles_w * p.tiles_h;
-  for (int i = 0; i < 2; ++i) { p.gn_part[i] = d.gn_part[i]; p.gn_cstride[i] = d.gn_cstride[i]; p.gn_coff[i] = d.gn_coff[i]; }
-  if (p.gn_part[0] == nullptr && p.gn_part[1] != nullptr) {
-    p.gn_part[0] = p.gn_part[1]; p.gn_cstride[0] = p.gn_cstride[1]; p.gn_coff[0] = p.gn_coff[1]; p.gn_part[1] = nullptr;
+  {
+    int k = 0;
+    p.sink[0] = GnSink{}; p.sink[1] = GnSink{};
+    for (int i = 0; i < 2; ++i) {
+      if (!d.sink[i].part) continue;
+      p.sink[k] = d.sink[i];
+      if (p.sink[k].expected == 0) p.sink[k].expected = (unsigned)(p.gn_slots * p.sink[k].cstride);
+      if (p.sink[k].eps == 0.f) p.sink[k].eps = 1e-5f;
+      ++k;
+    }
   }
   return 0;
 }

@@ -45,17 +45,16 @@ struct MlpParams {
   int hsplit;                        // 1, or 2: the hidden dimension is split over two CTA pairs of one cluster (few-tile
                                      // layers); each pair walks half of the chunks and the partial outputs are summed
                                      // through distributed shared memory, each pair finishing half of the E columns
-  float* gn_part[2]; int gn_cstride[2]; int gn_coff[2]; int gn_slots;
+  GnSink sink[2]; int gn_slots;      // fused GroupNorm statistics of the output (gn_stats.cuh)
   long long* dbg;                    // optional: CTA 0 writes a clock64 timeline [64 chunks][8] (profiling aid)
   // optional fused input GroupNorm (the Swin block's norm2, models/swin_transformer.py:279): X is then the UN-normalised
   // tensor and the CTA applies  a*x + b  (per image, per channel; plain affine, no FiLM / SiLU) to its X tile in
   // shared memory before the first GEMM — one gn_apply launch and one activation round trip less per Swin block.
-  // Statistics arrive as the producer's deterministic partial sums, exactly as gn_apply_kernel reads them.
-  const float* gn_in_part;           // [N][gn_in_slots][E][2] or nullptr
-  int gn_in_slots;
+  // Statistics arrive as the per-(image, group) pairs (mean, rstd) finalised by the producer (gn_stats.cuh), exactly
+  // as gn_apply_kernel reads them: the operand equals what the separate pass would have stored, bit for bit.
+  const float* gn_in_gstat;          // [N][32][2] or nullptr
   const float* gn_in_gamma;          // [E]
   const float* gn_in_beta;           // [E]
-  float gn_in_eps;
 };
 
 #ifdef __CUDACC__
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
     const bool el = elect_one();
     const uint32_t lead_x = mapa_u32(smem_u32(x_full), lead);
     if (el) {
-      if (p.gn_in_part) {
+      if (p.gn_in_gstat) {
         // fused input GroupNorm: each CTA's GELU warps wait for their OWN tile, normalise it, then signal the leader
         mbar_arrive_expect_tx(x_full, (uint32_t)(kx * kTile));
         for (int kb = 0; kb < kx; ++kb) tma_load_4d(sX + (size_t)kb * kTile, &p.tmX, x_full, kb * kConvBK, w0, h0, n0);
@@ -209,7 +208,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
         }
         if (dbg && el) dbg[c * 8 + 1] = clock64() - t_start;
       };
-      mbar_wait(p.gn_in_part ? x_ready : x_full, 0);
+      mbar_wait(p.gn_in_gstat ? x_ready : x_full, 0);
       tc_fence_after();
       gemm1(0);
       if (chunks > 1) gemm1(1);
@@ -248,55 +247,19 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
     const int r = quad * 32 + lane;
     const int etid = threadIdx.x;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    if (p.gn_in_part) {
+    if (p.gn_in_gstat) {
       // ---- fused input GroupNorm: statistics -> per-(image, channel) affine -> X tile normalised in place ----
       // (same arithmetic and summation order as gn_apply_kernel, so the operand equals what the separate pass stored)
       const int E = p.E, cpg = E / 32;
       const int nimg = p.bn;                                       // images this tile touches (1 or 2)
-      float* s_sum = s_b1;                                         // scratch [2][E][2] (bias1 is loaded afterwards)
-      float* s_mr = s_ab + 2 * E * 2;                              // [2][32][2]
-      for (int idx = etid; idx < nimg * E; idx += 32 * kMlpEpiWarps) {
-        const int img = idx / E, c = idx - img * E;
-        float sv = 0.f, qv = 0.f;
-        if (n0 + img < p.Nimg) {
-          const float* part = p.gn_in_part + (size_t)(n0 + img) * p.gn_in_slots * E * 2;
-          int sl = 0;
-          for (; sl + 16 <= p.gn_in_slots; sl += 16) {
-            float2 e[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) e[u] = *reinterpret_cast<const float2*>(part + ((size_t)(sl + u) * E + c) * 2);
-#pragma unroll
-            for (int u = 0; u < 16; ++u) { sv += e[u].x; qv += e[u].y; }
-          }
-          for (; sl + 4 <= p.gn_in_slots; sl += 4) {
-            float2 e[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) e[u] = *reinterpret_cast<const float2*>(part + ((size_t)(sl + u) * E + c) * 2);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { sv += e[u].x; qv += e[u].y; }
-          }
-          for (; sl < p.gn_in_slots; ++sl) {
-            const float2 e = *reinterpret_cast<const float2*>(part + ((size_t)sl * E + c) * 2);
-            sv += e.x; qv += e.y;
-          }
-        }
-        s_sum[(img * E + c) * 2] = sv; s_sum[(img * E + c) * 2 + 1] = qv;
-      }
-      named_bar_sync(1, 32 * kMlpEpiWarps);
-      if (etid < 32 * nimg) {
-        const int img = etid >> 5, g = etid & 31;
-        float sv = 0.f, qv = 0.f;
-        for (int j = 0; j < cpg; ++j) { sv += s_sum[(img * E + g * cpg + j) * 2]; qv += s_sum[(img * E + g * cpg + j) * 2 + 1]; }
-        const float inv_cnt = 1.0f / (float)((long long)cpg * p.Hout * p.Wout);
-        const float mean = sv * inv_cnt;
-        const float var = fmaxf(qv * inv_cnt - mean * mean, 0.f);
-        s_mr[(img * 32 + g) * 2] = mean; s_mr[(img * 32 + g) * 2 + 1] = rsqrtf(var + p.gn_in_eps);
-      }
-      named_bar_sync(1, 32 * kMlpEpiWarps);
       for (int idx = etid; idx < nimg * E; idx += 32 * kMlpEpiWarps) {
         const int img = idx / E, c = idx - img * E, g = c / cpg;
-        const float a = s_mr[(img * 32 + g) * 2 + 1] * __ldg(p.gn_in_gamma + c);
-        const float b = __ldg(p.gn_in_beta + c) - s_mr[(img * 32 + g) * 2] * a;
+        float a = 0.f, b = 0.f;
+        if (n0 + img < p.Nimg) {
+          const float2 mr = ldcg_f2(p.gn_in_gstat + ((size_t)(n0 + img) * 32 + g) * 2);
+          a = mr.y * __ldg(p.gn_in_gamma + c);
+          b = __ldg(p.gn_in_beta + c) - mr.x * a;
+        }
         s_ab[(img * E + c) * 2] = a; s_ab[(img * E + c) * 2 + 1] = b;
       }
       named_bar_sync(1, 32 * kMlpEpiWarps);
@@ -323,7 +286,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
       fence_proxy_async_smem();                                     // the tensor core reads X through the async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(x_ready), lead));
-      named_bar_sync(1, 32 * kMlpEpiWarps);                         // s_sum (aliasing the bias area) is free again
     }
     for (int i = etid; i < p.Hd; i += 32 * kMlpEpiWarps) s_b1[i] = __ldg(p.bias1 + i);
     for (int i = etid; i < p.E; i += 32 * kMlpEpiWarps) s_b2[i] = __ldg(p.bias2 + i);
@@ -387,7 +349,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
       }
     } else {
     const int lw = r % p.bw, lh = (r / p.bw) % p.bh, ln = r / (p.bw * p.bh);
-    const bool row_ok = (w0 + lw < p.Wout) && (h0 + lh < p.Hout) && (n0 + ln < p.Nimg);
     const int nblk = p.E >> 6;
     uint8_t* sblk = sX;                                  // X is dead: every MMA has retired
     float* wsum = reinterpret_cast<float*>(sH);          // [4 quads][E][2]
@@ -398,7 +359,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
       }
       mbar_wait(res_bar, 0);
     }
-    const bool want_stats = p.gn_part[0] != nullptr;
+    const bool want_stats = p.sink[0].part != nullptr;
     const uint32_t trow2 = tm_acc2 + lane_base;
     for (int c = cpar * 16; c < p.E; c += 64) {
       uint32_t v[16];
@@ -439,37 +400,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
         q1[i] = __floats2half2_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
       }
       *a0 = o0; *a1 = o1;
-      if (want_stats) {
-        float sv[16], sq[16];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 x0 = __half22float2(q0[i]);
-          const float2 x1 = __half22float2(q1[i]);
-          sv[2 * i] = x0.x; sv[2 * i + 1] = x0.y; sv[8 + 2 * i] = x1.x; sv[8 + 2 * i + 1] = x1.y;
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { if (!row_ok) sv[i] = 0.f; sq[i] = sv[i] * sv[i]; }
-#pragma unroll
-        for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-          const bool upper = (lane & bit) != 0;
-#pragma unroll
-          for (int i = 0; i < half; ++i) {
-            const float send_s = upper ? sv[i] : sv[i + half];
-            const float keep_s = upper ? sv[i + half] : sv[i];
-            sv[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
-            const float send_q = upper ? sq[i] : sq[i + half];
-            const float keep_q = upper ? sq[i + half] : sq[i];
-            sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
-          }
-        }
-        sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
-        sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
-        if ((lane & 1) == 0) {
-          const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          wsum[((size_t)quad * p.E + c + cidx) * 2] = sv[0];
-          wsum[((size_t)quad * p.E + c + cidx) * 2 + 1] = sq[0];
-        }
-      }
     }
     fence_proxy_async_smem();
     named_bar_sync(1, 32 * kMlpEpiWarps);
@@ -477,32 +407,19 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
       for (int bq = 0; bq < nblk; ++bq) tma_store_4d(&p.tmOut, sblk + (size_t)bq * kTile, bq * 64, w0, h0, n0);
       tma_store_commit();
     }
-    if (want_stats && n0 < p.Nimg) {
+    if (want_stats) {
+      float* wstat = wsum;                                           // [2 halves][E][2]
+      int* s_flag = reinterpret_cast<int*>(wstat + 4 * p.E);
+      staged_tile_column_stats(sblk, p.E, 64, etid, wstat);
+      named_bar_sync(1, 32 * kMlpEpiWarps);
       const int slot = th * p.tiles_w + tw;
-      for (int cc = etid; cc < p.E; cc += 32 * kMlpEpiWarps) {
-        const float s0 = wsum[((size_t)0 * p.E + cc) * 2], q0s = wsum[((size_t)0 * p.E + cc) * 2 + 1];
-        const float s1 = wsum[((size_t)1 * p.E + cc) * 2], q1s = wsum[((size_t)1 * p.E + cc) * 2 + 1];
-        const float s2 = wsum[((size_t)2 * p.E + cc) * 2], q2s = wsum[((size_t)2 * p.E + cc) * 2 + 1];
-        const float s3 = wsum[((size_t)3 * p.E + cc) * 2], q3s = wsum[((size_t)3 * p.E + cc) * 2 + 1];
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-          float* part = p.gn_part[d];
-          if (!part) continue;
-          const size_t ch = (size_t)p.gn_coff[d] + cc;
-          if (p.bn == 1) {
-            float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
-            dst[0] = (s0 + s1) + (s2 + s3);
-            dst[1] = (q0s + q1s) + (q2s + q3s);
-          } else {
-            float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
-            dst[0] = s0 + s1; dst[1] = q0s + q1s;
-            if (n0 + 1 < p.Nimg) {
-              float* dst1 = part + (((size_t)(n0 + 1) * p.gn_slots + slot) * p.gn_cstride[d] + ch) * 2;
-              dst1[0] = s2 + s3; dst1[1] = q2s + q3s;
-            }
-          }
-        }
-      }
+      if (n0 < p.Nimg)
+        write_tile_pairs(wstat, p.E, p.E, 0, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kMlpEpiWarps);
+      const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
+      const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
+      const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
+      const unsigned int ad[4] = {(unsigned)p.E, (unsigned)p.E, (unsigned)p.E, (unsigned)p.E};
+      gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kMlpEpiWarps, 1, s_flag);
     }
     if (etid == 0) tma_store_wait_read();
     }
@@ -554,41 +471,30 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
         }
         *reinterpret_cast<uint4*>(s_out + (size_t)rr * cw + cu * 8) = o;                  // zeros outside the tensor
       }
-      if (p.gn_part[0] != nullptr) {
+      if (p.sink[0].part != nullptr) {
         named_bar_sync(1, 32 * kMlpEpiWarps);
         for (int t = etid; t < 2 * cw; t += 32 * kMlpEpiWarps) {
           const int half = t / cw, c = t - half * cw;
-          float sv = 0.f, qv = 0.f;
-          for (int rr = half * 64; rr < half * 64 + 64; ++rr) {
-            const float v = __half2float(s_out[(size_t)rr * cw + c]);
-            sv += v; qv += v * v;
+          const __half* colp = s_out + (size_t)(half * 64) * cw + c;
+          const float pv = __half2float(colp[0]);
+          float s1 = 0.f, s2 = 0.f;
+          for (int rr = 1; rr < 64; ++rr) {
+            const float d = __half2float(colp[(size_t)rr * cw]) - pv;
+            s1 += d; s2 = fmaf(d, d, s2);
           }
-          s_col[(half * cw + c) * 2] = sv; s_col[(half * cw + c) * 2 + 1] = qv;
+          s_col[(half * cw + c) * 2] = pv + s1 * (1.0f / 64.0f);
+          s_col[(half * cw + c) * 2 + 1] = fmaxf(s2 - s1 * s1 * (1.0f / 64.0f), 0.f);
         }
         named_bar_sync(1, 32 * kMlpEpiWarps);
-        if (n0 < p.Nimg) {
-          const int slot = th * p.tiles_w + tw;
-          for (int c = etid; c < cw; c += 32 * kMlpEpiWarps) {
-            const int col = cbase + c;
-            const float sl = s_col[c * 2], ql = s_col[c * 2 + 1], sh = s_col[(cw + c) * 2], qh = s_col[(cw + c) * 2 + 1];
-#pragma unroll
-            for (int dI = 0; dI < 2; ++dI) {
-              float* part = p.gn_part[dI];
-              if (!part) continue;
-              const size_t ch = (size_t)p.gn_coff[dI] + col;
-              float* dst = part + (((size_t)n0 * p.gn_slots + slot) * p.gn_cstride[dI] + ch) * 2;
-              if (p.bn == 1) {
-                dst[0] = sl + sh; dst[1] = ql + qh;
-              } else {
-                dst[0] = sl; dst[1] = ql;
-                if (n0 + 1 < p.Nimg) {
-                  float* dst1 = part + (((size_t)(n0 + 1) * p.gn_slots + slot) * p.gn_cstride[dI] + ch) * 2;
-                  dst1[0] = sh; dst1[1] = qh;
-                }
-              }
-            }
-          }
-        }
+        const int slot = th * p.tiles_w + tw;
+        if (n0 < p.Nimg)
+          write_tile_pairs(s_col, cw, cw, cbase, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kMlpEpiWarps);
+        int* s_flag = reinterpret_cast<int*>(s_col + 4 * cw);
+        const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
+        const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
+        const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
+        const unsigned int ad[4] = {(unsigned)cw, (unsigned)cw, (unsigned)cw, (unsigned)cw};
+        gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kMlpEpiWarps, 1, s_flag);
       }
     }
   }
