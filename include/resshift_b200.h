@@ -47,6 +47,21 @@ typedef struct rs_unet_config {
   int32_t lq_size;
 } rs_unet_config;
 
+/* ``autoencoder.params`` of the shipped yaml files: VQModelTorch(ddconfig, n_embed, embed_dim)
+ * (reference ldm/models/autoencoder.py:12-26; ddconfig -> ldm/modules/diffusionmodules/model.py:452-470,563-581).
+ * Covered: double_z = False, attn_resolutions = [], dropout = 0 (every shipped config). */
+typedef struct rs_vq_config {
+  int32_t embed_dim;
+  int32_t n_embed;
+  int32_t z_channels;
+  int32_t in_channels;
+  int32_t out_ch;
+  int32_t ch;
+  int32_t n_levels;
+  int32_t ch_mult[RS_MAX_LEVELS];
+  int32_t num_res_blocks[RS_MAX_LEVELS];
+} rs_vq_config;
+
 typedef struct rs_engine rs_engine;     /* architecture + packed weights      */
 typedef struct rs_plan rs_plan;         /* engine bound to (batch, H, W)      */
 typedef struct rs_sampler rs_sampler;   /* plan + diffusion schedule (T steps) */
@@ -109,6 +124,35 @@ int rs_sampler_run_host(rs_sampler* s, const float* z_y_host, const float* noise
 size_t rs_sampler_staging_bytes(const rs_sampler* s);
 /* optional taps for parity tests: per-step pred_xstart / sample, [T, B, C, H, W] fp32 device buffers or NULL */
 int rs_sampler_set_taps(rs_sampler* s, float* pred_xstart_steps, float* sample_steps);
+
+/* ---- VQ-GAN first stage: ldm.models.autoencoder.VQModelTorch (reference ldm/models/autoencoder.py:12-47) -------
+ * The engine handle is the same opaque type as the denoiser's: rs_unet_param_count / _param_info / _arena_bytes /
+ * _set_arena / _load_param work on it unchanged (state_dict names and shapes of the reference's VQModelTorch, so
+ * autoencoder_vq_f4.pth / ffhq512_vq_f8_dim8_face.pth load as they are). */
+int rs_vq_create(const rs_vq_config* cfg, rs_engine** out);
+/* plan for a fixed (batch, image H, image W); which = 0: encode (image -> latent), 1: decode (latent -> image).
+ * Uses rs_plan_workspace_bytes / rs_plan_bind / rs_plan_destroy like a denoiser plan. */
+int rs_vq_plan_create(rs_engine* e, int batch, int image_h, int image_w, int which, rs_plan** out);
+/* VQModelTorch.encode (autoencoder.py:28-31): x [B, 3, H, W] fp32 -> h [B, embed_dim, H/f, W/f] fp32 (f = 2^(levels-1)) */
+int rs_vq_encode(rs_plan* p, const float* x, float* h_out, void* stream);
+/* VQModelTorch.decode (autoencoder.py:33-40): h [B, embed_dim, H/f, W/f] -> quantize (VectorQuantizer2,
+ * ldm/modules/vqvae/quantize.py:271-284; skipped when force_not_quantize) -> post_quant_conv -> Decoder -> [B, 3, H, W] fp32.
+ * idx_out: optional [B, H/f, W/f] int32 code indices. */
+int rs_vq_decode(rs_plan* p, const float* h, float* out, int32_t* idx_out, int force_not_quantize, void* stream);
+
+/* ---- image edges of the sampler (reference sampler.py:176-223,286; utils/util_image.py:216-273,889-979) --------- */
+/* F.interpolate(x, scale_factor=sf, mode='bicubic') on fp32 NCHW (models/gaussian_diffusion.py:503-504) */
+int rs_op_bicubic_upsample(const float* x, int N, int C, int H, int W, int sf, float* y, void* stream);
+/* uint8 HWC image(s) -> fp32 NCHW in [-1, 1]: (v / 255 - 0.5) / 0.5 */
+int rs_op_ingest_u8(const void* src_u8_nhwc, int N, int H, int W, int C, float* dst_nchw, void* stream);
+/* fp32 NCHW in [-1, 1] -> clamp, * 0.5 + 0.5, optional mask-back blend with lq (mask = 1 keeps the model output),
+ * round(v * 255) -> uint8 HWC in RGB (bgr = 0) or BGR (bgr = 1) order (util_image.tensor2img) */
+int rs_op_emit_u8(const float* sr_nchw, const float* lq_nchw_or_null, const float* mask_or_null, int N, int H, int W,
+                  int bgr, void* dst_u8_nhwc, void* stream);
+/* overlap-average of tiled results (ImageSpliterTh.update / gather): tiles [nty*ntx, N, C, th, tw] fp32 at output
+ * origins ys[nty] / xs[ntx] (device int32 arrays) -> out [N, C, H, W] */
+int rs_op_tile_gather(const float* tiles, int N, int C, int H, int W, int th, int tw, int nty, int ntx, const int32_t* ys,
+                      const int32_t* xs, float* out, void* stream);
 
 /* ---- single operators (unit tests / reuse) --------------------------------------------------- */
 /* p_sample update (reference models/gaussian_diffusion.py:361-364 with :218-221) */

@@ -31,6 +31,15 @@ class UNetConfigC(C.Structure):
     ]
 
 
+class VQConfigC(C.Structure):
+    """Mirror of ``rs_vq_config``."""
+    _fields_ = [
+        ("embed_dim", C.c_int32), ("n_embed", C.c_int32), ("z_channels", C.c_int32), ("in_channels", C.c_int32),
+        ("out_ch", C.c_int32), ("ch", C.c_int32), ("n_levels", C.c_int32),
+        ("ch_mult", C.c_int32 * RS_MAX_LEVELS), ("num_res_blocks", C.c_int32 * RS_MAX_LEVELS),
+    ]
+
+
 # every symbol include/resshift_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
 _SIGNATURES = {
@@ -81,6 +90,14 @@ _SIGNATURES = {
     "rs_op_mlp": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rs_debug_tile_config": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "rs_op_upsample2x": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "rs_vq_create": (C.c_int, [C.POINTER(VQConfigC), C.POINTER(_P)]),
+    "rs_vq_plan_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "rs_vq_encode": (C.c_int, [_P, _P, _P, _P]),
+    "rs_vq_decode": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
+    "rs_op_bicubic_upsample": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "rs_op_ingest_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "rs_op_emit_u8": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "rs_op_tile_gather": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
 }
 
 
@@ -134,4 +151,16 @@ def make_config(cfg) -> UNetConfigC:
     c.swin_depth, c.swin_embed_dim, c.swin_heads = cfg.swin_depth, cfg.swin_embed_dim, cfg.swin_heads
     c.window_size, c.mlp_ratio = cfg.window_size, float(cfg.mlp_ratio)
     c.cond_mask, c.lq_size = int(cfg.cond_mask), cfg.lq_size
+    return c
+
+
+def make_vq_config(cfg) -> VQConfigC:
+    c = VQConfigC()
+    c.embed_dim, c.n_embed, c.z_channels = cfg.embed_dim, cfg.n_embed, cfg.z_channels
+    c.in_channels, c.out_ch, c.ch = cfg.in_channels, cfg.out_ch, cfg.ch
+    c.n_levels = len(cfg.ch_mult)
+    for i, v in enumerate(cfg.ch_mult):
+        c.ch_mult[i] = int(v)
+    for i, v in enumerate(cfg.num_res_blocks):
+        c.num_res_blocks[i] = int(v)
     return c

@@ -117,7 +117,7 @@ def preset(name: str, steps: Optional[int] = None) -> Tuple[UNetConfig, Diffusio
         # configs/realsr_swinunet_realesrgan256.yaml: T=15, min_noise_level 0.04
         u = UNetConfig()
         d = DiffusionConfig()
-    elif name in ("realsr_journal", "realsr_swinunet_realesrgan256_journal"):
+    elif name in ("realsr_journal", "realsr_swinunet_realesrgan256_journal", "v3", "realsr_v3"):
         # configs/realsr_swinunet_realesrgan256_journal.yaml:38-73 (T=4 native)
         u = UNetConfig()
         d = DiffusionConfig(min_noise_level=0.2, steps=4)
@@ -128,9 +128,15 @@ def preset(name: str, steps: Optional[int] = None) -> Tuple[UNetConfig, Diffusio
         # configs/faceir_gfpgan512_lpips.yaml: f8 VQ (8 latent channels), LQ at 512
         u = UNetConfig(in_channels=8, out_channels=8, lq_size=512)
         d = DiffusionConfig(sf=1, min_noise_level=0.2, steps=4)
-    elif name in ("inpaint", "inpaint_lama256_imagenet"):
+    elif name in ("inpaint", "inpaint_imagenet", "inpaint_lama256_imagenet", "inpaint_face", "inpaint_lama256_face"):
+        # configs/inpaint_lama256_imagenet.yaml and inpaint_lama256_face.yaml: identical denoiser / schedule; they differ in
+        # the VQ-GAN checkpoint only (autoencoder_vq_f4.pth vs celeba256_vq_f4_dim3_face.pth, same f4 architecture)
         u = UNetConfig(cond_mask=True, lq_size=256)
         d = DiffusionConfig(sf=1, min_noise_level=0.2, steps=4)
+    elif name in ("realsr_x2", "realsr_realesrgan256_x2"):
+        # configs/realsr_realesrgan256_x2.yaml: x2 SR — the LQ image enters at 128x128 through a one-stage feature extractor
+        u = UNetConfig(lq_size=128)
+        d = DiffusionConfig(sf=2, min_noise_level=0.2, steps=4)
     elif name == "tiny":
         # not a shipped config: a narrow model with the same topology, for fast tests
         u = UNetConfig(model_channels=32, swin_embed_dim=64)
@@ -147,3 +153,16 @@ def preset(name: str, steps: Optional[int] = None) -> Tuple[UNetConfig, Diffusio
     if steps is not None:
         d.steps = steps
     return u, d
+
+
+def preset_vq_name(name: str) -> str:
+    """VQ-GAN architecture (resshift_b200.vq_arch.vq_preset) each task's yaml names in its `autoencoder:` block."""
+    return "f8_face" if name in ("faceir", "faceir_gfpgan512_lpips", "tiny_faceir") else "f4"
+
+
+# inference_resshift.py --task / --version -> preset (reference inference_resshift.py:15-35,77-126)
+TASKS = {
+    ("realsr", "v1"): "realsr", ("realsr", "v2"): "realsr", ("realsr", "v3"): "realsr_journal",
+    ("bicsr", None): "bicsr", ("inpaint_imagenet", None): "inpaint_imagenet", ("inpaint_face", None): "inpaint_face",
+    ("faceir", None): "faceir",
+}

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
   uint64_t* acc_empty = acc_full + 2;              // [2] leader's: one arrival per epilogue warp (of both CTAs)
   uint64_t* res_bar = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  GnArriveList* alist = reinterpret_cast<GnArriveList*>(tmem_slot + 2);   // deferred GroupNorm arrivals (gn_stats.cuh)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
       const int c0 = (u % p.n_tiles) * p.BN;
       for (int c = etid; c < p.BN; c += 32 * kConvEpiWarps) dst[c] = (p.bias && c0 + c < p.Cout) ? __ldg(p.bias + c0 + c) : 0.f;
     };
+    if (etid == 0) { alist->cnt = 0; alist->over = 0; }
     if (worker < p.num_units) load_bias(worker, s_bias0);          // visible after the first tile's opening barrier
     for (int u = worker; u < p.num_units; u += num_workers, ++i) {
       const int b = i & 1;
@@ -269,20 +271,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
       if (want_stats) {
         // column statistics of the staged (fp16-rounded) tile, read back from shared memory while its TMA store drains
         float* wstat = wsum;                                         // [2 halves][BN][2]
-        int* s_flag = reinterpret_cast<int*>(wstat + 4 * p.BN);
         staged_tile_column_stats(s_stage, p.BN, bc, etid, wstat);
         named_bar_sync(1, 32 * kConvEpiWarps);
         const int ncols = min(p.BN, p.Cout - col0);
         const int slot = th * p.tiles_w + tw;
-        if (n0 < p.Nimg)                                             // (else: padding tile of an odd pair)
+        if (n0 < p.Nimg) {                                           // (else: padding tile of an odd pair)
           write_tile_pairs(wstat, p.BN, ncols, col0, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kConvEpiWarps);
-        const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
-        const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
-        const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
-        const unsigned int ad[4] = {(unsigned)ncols, (unsigned)ncols, (unsigned)ncols, (unsigned)ncols};
-        gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kConvEpiWarps, 1, s_flag);
+          if (etid == 0) {                                           // arrivals are batched: one round after the last tile
+#pragma unroll
+            for (int d = 0; d < 2; ++d)
+              if (p.sink[d].part && p.sink[d].gstat) {
+                gn_list_add(alist, d, n0, (unsigned)ncols);
+                if (p.bn == 2 && n0 + 1 < p.Nimg) gn_list_add(alist, d, n0 + 1, (unsigned)ncols);
+              }
+          }
+        }
       }
     }
+    if (want_stats) gn_list_arrive(alist, p.sink[0], p.sink[1], p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kConvEpiWarps, 1);
     if (etid == 0) tma_store_wait_read();
   }
 

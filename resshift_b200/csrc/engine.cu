@@ -16,6 +16,7 @@
 
 #include "../../include/resshift_b200.h"
 #include "launch.cuh"
+#include "vq_kernels.cuh"
 
 namespace rs {
 
@@ -25,7 +26,7 @@ int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-enum Role { R_CONV3 = 0, R_CONV1, R_LINEAR, R_BIAS, R_GN_W, R_GN_B, R_RELPOS, R_BUF_RELIDX, R_BUF_MASK };
+enum Role { R_CONV3 = 0, R_CONV1, R_LINEAR, R_BIAS, R_GN_W, R_GN_B, R_RELPOS, R_BUF_RELIDX, R_BUF_MASK, R_F32 /* fp32 tensor kept as is (VQ codebook) */ };
 
 struct Param {
   std::string name;
@@ -41,6 +42,8 @@ struct Param {
 using namespace rs;
 
 struct rs_engine {
+  int kind = 0;                 // 0: UNetModelSwin denoiser, 1: VQ-GAN first stage (vq.inc); the parameter store is shared
+  rs_vq_config vq{};
   rs_unet_config cfg;
   std::vector<Param> params;
   std::map<std::string, int> index;
@@ -254,7 +257,7 @@ int build_inventory(rs_engine& e) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-enum OpKind { OP_CONV, OP_GN, OP_ATTN, OP_UPSAMPLE, OP_MLP };
+enum OpKind { OP_CONV, OP_GN, OP_ATTN, OP_UPSAMPLE, OP_MLP, OP_SOFTMAX };
 
 struct Tensor {
   size_t bytes = 0;
@@ -271,6 +274,12 @@ struct Op {
   View a_in, a_out; const float* a_bias = nullptr; int a_shift = 0;
   // upsample
   View u_in, u_out;
+  // row softmax (VQ-GAN attention): in place on s_view [rows = N*H*W][cols = C]
+  View s_view; float s_scale = 1.f;
+  // conv whose "weight" matrix is an activation tensor of the plan (per-image attention GEMMs), or whose INPUT is a
+  // weight matrix of the arena viewed as pixels (the transposed value projection): see vq.inc
+  View w_view; bool w_is_view = false;
+  std::string in_param;
   // fused MLP
   MlpDesc mlp;
   std::string w2_name, b2_name;
@@ -304,6 +313,8 @@ struct rs_plan {
   float* out_f32 = nullptr;  // model output (fp32 NCHW), inside the state region
   bool bound = false;
   int launches = 0;
+  int vq_which = -1;         // -1: denoiser plan; 0 / 1: VQ-GAN encode / decode plan (vq.inc)
+  int imgH = 0, imgW = 0;    // VQ plans: image size (H, W above are the latent size)
   // The schedule tables and the FiLM table live in this plan's workspace and are shared by rs_plan_forward (FiLM rows
   // 0..B-1 for the caller's timesteps) and by every sampler of the plan (rows 0..T-1 for its schedule): whoever wrote them
   // last owns them.  A sampler re-derives them when it is not the owner or when the weights changed since (weights_epoch).
@@ -354,9 +365,10 @@ struct Builder {
   int opi() const { return (int)(P.fe_ops.size() + P.ops.size()); }
 
   void conv(const View& in, const std::string& name, int ksize, int stride, int cout, const View* out,
-            const View* res, int act, bool out_f32 = false) {
+            const View* res, int act, bool out_f32 = false, int pad_lo = 1) {
     Op op; op.kind = OP_CONV;
     op.conv.in = in; op.conv.ksize = ksize; op.conv.stride = stride; op.conv.Cout = cout; op.conv.act = act;
+    op.conv.pad_lo = pad_lo;
     if (out) { op.conv.out = *out; op.conv.has_out = true; } else op.conv.has_out = false;
     if (res) { op.conv.res = *res; op.conv.has_res = true; }
     op.w_name = name + ".weight"; op.b_name = name + ".bias";
@@ -381,9 +393,9 @@ struct Builder {
       ws.push_back({out->off, cout, list_id(), (int)cur->size() - 1});
     }
   }
-  void gn(const View& in, const std::string& name, const View& out, int silu, int film_off) {
+  void gn(const View& in, const std::string& name, const View& out, int silu, int film_off, float eps = 1e-5f) {
     Op op; op.kind = OP_GN;
-    op.gn.in = in; op.gn.out = out; op.gn.silu = silu; op.gn.film_off = film_off;
+    op.gn.in = in; op.gn.out = out; op.gn.silu = silu; op.gn.film_off = film_off; op.gn.eps = eps;
     op.g_name = name;
     // can the producers' epilogues deliver the statistics?  (every channel of the view written by a conv of this plan)
     bool fusable = false;
@@ -555,6 +567,62 @@ struct Builder {
   }
 };
 
+// Workspace layout shared by the denoiser plan and the VQ-GAN plans (vq.inc): fixed regions, then persistent tensors,
+// then liveness-packed temporaries.  `state_bytes` = one fp32 latent / output image; the denoiser keeps two (x_t, model out).
+int finish_layout(rs_plan& P, Builder& b, size_t state_bytes, bool unet) {
+  rs_engine& E = *P.e;
+  const rs_unet_config& c = E.cfg;
+  const int B = P.B;
+  P.max_rows = std::max(B, 64);
+  size_t off = 0;
+  auto region = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  if (unet) {
+    P.off_tables = region(4 * 1024 * sizeof(float));                   // coef1, coef2, std, in_scale (<= 1024 steps)
+    P.off_tsteps = region((size_t)P.max_rows * sizeof(float));
+    P.off_emb_sin = region((size_t)P.max_rows * c.model_channels * sizeof(float));
+    P.off_emb_mid = region((size_t)P.max_rows * E.time_dim() * sizeof(float));
+    P.off_emb_vec = region((size_t)P.max_rows * E.time_dim() * sizeof(float));
+    P.off_film = region((size_t)P.max_rows * E.film_rows * sizeof(float));
+  }
+  P.stats_bytes = b.stats_off;
+  P.off_stats = region(P.stats_bytes);
+  P.n_gn = b.n_gn;
+  P.off_gstat = region((size_t)P.n_gn * B * 32 * 2 * sizeof(float));
+  P.off_counters = region((size_t)P.n_gn * B * sizeof(unsigned int));
+  // sampler state: x_t (fp32), model output / pred_xstart (fp32)
+  const size_t lat = state_bytes;
+  P.off_state = region(2 * align_up(lat, 256));
+  // persistent tensors first, then liveness-packed temporaries (RS_NO_REUSE=1 keeps every tensor
+  // alive for the whole forward so that rs_plan_probe can read any block output afterwards)
+  if (env_int("RS_NO_REUSE", 0)) for (Tensor& tz : P.tensors) tz.persistent = true;
+  for (Tensor& tz : P.tensors) if (tz.persistent) tz.off = region(tz.bytes);
+  P.off_temps = off;
+  {
+    struct Live { size_t off, bytes; int last; };
+    std::vector<Live> live;
+    std::vector<int> order;
+    for (int i = 0; i < (int)P.tensors.size(); ++i) if (!P.tensors[i].persistent && P.tensors[i].last >= 0) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int bb) { return P.tensors[a].first < P.tensors[bb].first; });
+    size_t high = 0;
+    for (int id : order) {
+      Tensor& tz = P.tensors[id];
+      live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.last < tz.first; }), live.end());
+      std::sort(live.begin(), live.end(), [](const Live& a, const Live& bb) { return a.off < bb.off; });
+      size_t pos = 0;
+      for (const Live& l : live) {
+        if (pos + tz.bytes <= l.off) break;
+        pos = std::max(pos, l.off + l.bytes);
+      }
+      tz.off = P.off_temps + pos;
+      live.push_back({pos, tz.bytes, tz.last});
+      high = std::max(high, pos + tz.bytes);
+    }
+    P.temps_bytes = high;
+  }
+  P.workspace_bytes = align_up(P.off_temps + P.temps_bytes, 256);
+  return 0;
+}
+
 int build_plan(rs_plan& P) {
   rs_engine& E = *P.e;
   const rs_unet_config& c = E.cfg;
@@ -645,53 +713,7 @@ int build_plan(rs_plan& P) {
   b.gn(final_h, "out.0", t, 1, -1);
   b.conv(t, "out.2", 3, 1, c.out_channels, nullptr, nullptr, ACT_NONE, /*out_f32=*/true);
 
-  // ---- workspace layout ------------------------------------------------------------------------
-  P.max_rows = std::max(B, 64);
-  size_t off = 0;
-  auto region = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  P.off_tables = region(4 * 1024 * sizeof(float));                   // coef1, coef2, std, in_scale (<= 1024 steps)
-  P.off_tsteps = region((size_t)P.max_rows * sizeof(float));
-  P.off_emb_sin = region((size_t)P.max_rows * c.model_channels * sizeof(float));
-  P.off_emb_mid = region((size_t)P.max_rows * E.time_dim() * sizeof(float));
-  P.off_emb_vec = region((size_t)P.max_rows * E.time_dim() * sizeof(float));
-  P.off_film = region((size_t)P.max_rows * E.film_rows * sizeof(float));
-  P.stats_bytes = b.stats_off;
-  P.off_stats = region(P.stats_bytes);
-  P.n_gn = b.n_gn;
-  P.off_gstat = region((size_t)P.n_gn * B * 32 * 2 * sizeof(float));
-  P.off_counters = region((size_t)P.n_gn * B * sizeof(unsigned int));
-  // sampler state: x_t (fp32), model output / pred_xstart (fp32)
-  const size_t lat = (size_t)B * std::max(c.in_channels, c.out_channels) * P.H * P.W * sizeof(float);
-  P.off_state = region(2 * align_up(lat, 256));
-  // persistent tensors first, then liveness-packed temporaries (RS_NO_REUSE=1 keeps every tensor
-  // alive for the whole forward so that rs_plan_probe can read any block output afterwards)
-  if (env_int("RS_NO_REUSE", 0)) for (Tensor& tz : P.tensors) tz.persistent = true;
-  for (Tensor& tz : P.tensors) if (tz.persistent) tz.off = region(tz.bytes);
-  P.off_temps = off;
-  {
-    struct Live { size_t off, bytes; int last; };
-    std::vector<Live> live;
-    std::vector<int> order;
-    for (int i = 0; i < (int)P.tensors.size(); ++i) if (!P.tensors[i].persistent && P.tensors[i].last >= 0) order.push_back(i);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int bb) { return P.tensors[a].first < P.tensors[bb].first; });
-    size_t high = 0;
-    for (int id : order) {
-      Tensor& tz = P.tensors[id];
-      live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.last < tz.first; }), live.end());
-      std::sort(live.begin(), live.end(), [](const Live& a, const Live& bb) { return a.off < bb.off; });
-      size_t pos = 0;
-      for (const Live& l : live) {
-        if (pos + tz.bytes <= l.off) break;
-        pos = std::max(pos, l.off + l.bytes);
-      }
-      tz.off = P.off_temps + pos;
-      live.push_back({pos, tz.bytes, tz.last});
-      high = std::max(high, pos + tz.bytes);
-    }
-    P.temps_bytes = high;
-  }
-  P.workspace_bytes = align_up(P.off_temps + P.temps_bytes, 256);
-  return 0;
+  return finish_layout(P, b, (size_t)B * std::max(c.in_channels, c.out_channels) * P.H * P.W * sizeof(float), true);
 }
 
 void resolve(rs_plan& P, View& v) {
@@ -721,9 +743,20 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       }
       ConvDesc& d = op.conv;
       resolve(P, d.in); if (d.has_out) resolve(P, d.out); if (d.has_res) resolve(P, d.res);
-      const Param* w = E.find(op.w_name);
-      RS_CHECK(w != nullptr, "missing parameter " + op.w_name);
-      d.wt = E.at<__half>(op.w_name); d.ipad = w->ipad; d.bias = E.at<float>(op.b_name);
+      if (!op.in_param.empty()) {          // the "pixels" are the rows of a weight matrix of the arena
+        const Param* wp = E.find(op.in_param);
+        RS_CHECK(wp != nullptr && wp->ipad == d.in.ld, "missing / mismatching parameter " + op.in_param);
+        d.in.ptr = E.at<__half>(op.in_param);
+      }
+      if (op.w_is_view) {                  // the "weights" are an activation tensor [Cout rows][K], K-major
+        resolve(P, op.w_view);
+        d.wt = op.w_view.ptr; d.ipad = op.w_view.ld;
+        d.bias = op.b_name.empty() ? nullptr : E.at<float>(op.b_name);
+      } else {
+        const Param* w = E.find(op.w_name);
+        RS_CHECK(w != nullptr, "missing parameter " + op.w_name);
+        d.wt = E.at<__half>(op.w_name); d.ipad = w->ipad; d.bias = E.at<float>(op.b_name);
+      }
       d.out_f32 = op.to_f32 ? P.out_f32 : nullptr;
       d.partial = op.split_tens >= 0 ? reinterpret_cast<float*>(P.ws + P.tensors[op.split_tens].off) : nullptr;
       // the first conv reads the channel-padded packed input: expose the padded width to the kernel
@@ -767,6 +800,10 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       op.a_bias = E.at<float>(op.w_name);
       RS_CHECK(op.a_bias != nullptr, "missing " + op.w_name);
       ++P.launches;
+    } else if (op.kind == OP_SOFTMAX) {
+      resolve(P, op.s_view);
+      RS_CHECK(op.s_view.C % 8 == 0 && op.s_view.C <= 8192 && op.s_view.ld % 8 == 0, "softmax row length");
+      ++P.launches;
     } else {
       resolve(P, op.u_in); resolve(P, op.u_out);
       ++P.launches;
@@ -798,6 +835,7 @@ inline bool op_skipped(const Op& op) {
     case OP_ATTN: return (skip >> 3) & 1;
     case OP_UPSAMPLE: return (skip >> 4) & 1;
     case OP_MLP: return (skip >> 5) & 1;
+    case OP_SOFTMAX: return false;
   }
   return false;
 }
@@ -820,6 +858,12 @@ int run_ops(rs_plan& P, const std::vector<Op>& ops, const float* film_base, long
       case OP_ATTN:
         rc = attn_launch(op.a_in, op.a_out, op.a_bias, P.e->cfg.swin_heads, P.e->cfg.swin_embed_dim, op.a_shift, st);
         break;
+      case OP_SOFTMAX: {
+        SoftmaxParams sp{op.s_view.ptr, (long long)op.s_view.ld, op.s_view.N * op.s_view.H * op.s_view.W, op.s_view.C, op.s_scale};
+        (void)launch_k(softmax_rows_kernel, dim3((unsigned)sp.rows), dim3(256), (size_t)0, st, sp);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(-2, "softmax launch failed");
+        break;
+      }
       case OP_UPSAMPLE: {
         UpsampleParams u{op.u_in.ptr, op.u_in.sN(), op.u_in.ld, op.u_out.ptr, op.u_in.N, op.u_in.H, op.u_in.W, op.u_in.C};
         const long long total = (long long)u.N * 4 * u.H * u.W * (u.C / 8);
@@ -942,7 +986,8 @@ int rs_unet_load_param(rs_engine* e, const char* name, const float* src, void* s
     (void)launch_k(expand_relpos_kernel, dim3((e->cfg.swin_heads * 4096 + 255) / 256), dim3(256), (size_t)(0), st,
         src, reinterpret_cast<float*>(e->arena + p->off), e->cfg.swin_heads);
   } else {
-    const long long n = p->shape[0];
+    long long n = 1;
+    for (int v : p->shape) n *= v;
     (void)launch_k(copy_f32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), st, src, reinterpret_cast<float*>(e->arena + p->off), n);
   }
   RS_CUDA_OK(cudaGetLastError());
@@ -951,6 +996,7 @@ int rs_unet_load_param(rs_engine* e, const char* name, const float* src, void* s
 
 int rs_plan_create(rs_engine* e, int batch, int height, int width, rs_plan** out) {
   RS_CHECK(e && out && batch > 0, "bad argument");
+  RS_CHECK(e->kind == 0, "this engine is a VQ-GAN first stage: use rs_vq_plan_create");
   const int down = 1 << (e->cfg.n_levels - 1);
   RS_CHECK(height % (8 * down) == 0 && width % (8 * down) == 0,
            "latent H and W must be multiples of window_size * 2^(levels-1) (64 for the shipped configs)");
@@ -968,8 +1014,12 @@ int rs_plan_bind(rs_plan* p, void* workspace_dev) {
   RS_CHECK(p && workspace_dev && (reinterpret_cast<uintptr_t>(workspace_dev) & 255) == 0, "workspace must be 256-byte aligned");
   RS_CHECK(p->e->arena != nullptr, "rs_unet_set_arena before binding a plan");
   p->ws = static_cast<uint8_t*>(workspace_dev);
-  const size_t lat = align_up((size_t)p->B * std::max(p->e->cfg.in_channels, p->e->cfg.out_channels) * p->H * p->W * 4, 256);
-  p->out_f32 = reinterpret_cast<float*>(p->ws + p->off_state + lat);
+  if (p->vq_which >= 0) {
+    p->out_f32 = reinterpret_cast<float*>(p->ws + p->off_state);
+  } else {
+    const size_t lat = align_up((size_t)p->B * std::max(p->e->cfg.in_channels, p->e->cfg.out_channels) * p->H * p->W * 4, 256);
+    p->out_f32 = reinterpret_cast<float*>(p->ws + p->off_state + lat);
+  }
   resolve(*p, p->xin);
   if (p->fe_in.tens >= 0) { resolve(*p, p->fe_in); resolve(*p, p->lq_feat); }
   for (auto& kv : p->block_out) resolve(*p, kv.second);
@@ -977,7 +1027,7 @@ int rs_plan_bind(rs_plan* p, void* workspace_dev) {
   int rc = conv_init(); if (rc) return rc;
   rc = bind_ops(*p, p->fe_ops); if (rc) return rc;
   rc = bind_ops(*p, p->ops); if (rc) return rc;
-  p->launches += 6;   // embedding (4) + pack (1-2)
+  p->launches += p->vq_which >= 0 ? 3 : 6;   // denoiser: embedding (4) + pack (1-2); VQ: counter reset, pack / quantise, output copy
   p->bound = true;
   return 0;
 }
@@ -985,6 +1035,7 @@ int rs_plan_bind(rs_plan* p, void* workspace_dev) {
 int rs_plan_forward(rs_plan* p, const float* x, const float* timesteps, const float* lq, const float* mask, float* out,
                     void* stream) {
   RS_CHECK(p && p->bound, "plan is not bound");
+  RS_CHECK(p->vq_which < 0, "this is a VQ-GAN plan: use rs_vq_encode / rs_vq_decode");
   RS_CHECK(x && timesteps && lq && out, "null tensor");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->table_owner = nullptr;                       // FiLM rows 0..B-1 are overwritten below
@@ -1003,7 +1054,7 @@ int rs_plan_forward(rs_plan* p, const float* x, const float* timesteps, const fl
 // algorithmic FLOPs (2*MACs on real, un-padded channels) executed by the conv kernel in that forward.
 int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const float* lq, const float* mask,
                     double* ms_by_kind, double* conv_flops, int32_t* n_conv_launches, void* stream) {
-  RS_CHECK(p && p->bound && ms_by_kind, "bad argument");
+  RS_CHECK(p && p->bound && ms_by_kind && p->vq_which < 0, "bad argument (needs a bound denoiser plan)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p->table_owner = nullptr;
   int rc = run_embedding(*p, timesteps, p->B, st); if (rc) return rc;
@@ -1171,6 +1222,7 @@ extern "C" {
 
 int rs_sampler_create(rs_plan* p, int steps, const double* sqrt_etas, double kappa, const int32_t* tmap, rs_sampler** out) {
   RS_CHECK(p && p->bound && sqrt_etas && out, "bad argument (plan must be bound)");
+  RS_CHECK(p->vq_which < 0, "samplers are built on denoiser plans");
   RS_CHECK(steps >= 2 && steps <= p->max_rows && steps <= 1024, "steps out of range for this plan");
   auto s = std::make_unique<rs_sampler>();
   s->p = p; s->T = steps; s->kappa = kappa;
@@ -1289,4 +1341,5 @@ int rs_p_sample(const float* x_t, const float* x0, const float* noise, float* x_
 
 }  // extern "C"
 
+#include "vq.inc"
 #include "ops_api.inc"

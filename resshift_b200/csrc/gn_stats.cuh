@@ -41,6 +41,17 @@ __device__ __forceinline__ float2 ldcg_f2(const float* p) {
   return v;
 }
 
+// counter += v with acquire-release semantics at GPU scope, by ONE thread after a CTA barrier: the barrier orders the
+// other threads' pair stores before it (causality is cumulative over bar.sync), the release half publishes them, and —
+// if this turns out to be the last arrival — the acquire half orders the finaliser's reads after every earlier arrival.
+// (Each thread issuing __threadfence() instead costs MEMBAR.SC.GPU + CCTL.IVALL x 256 threads per tile: measured
+// +50 % on the stats-bearing 3x3 layers, profiles/r2_s1_*.)
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+
 // Combine two (count, mean, M2) triples with equal counts n each (Chan et al.): used for the two 64-row halves of a tile.
 __device__ __forceinline__ void chan_merge_equal(float n, float m0, float q0, float m1, float q1, float& m, float& q) {
   m = 0.5f * (m0 + m1);
@@ -48,78 +59,133 @@ __device__ __forceinline__ void chan_merge_equal(float n, float m0, float q0, fl
   q = q0 + q1 + n * (d0 * d0 + d1 * d1);
 }
 
-// Group statistics of image `n` from the per-(slot, channel) pairs: called by ONE warp per group with all 32 lanes.
-// K = slots * cpg items of `ns` values each.  Single pass around the pivot item 0; lanes take items lane, lane + 32, ...
-// and the lane partials are combined with a fixed shuffle tree.
-__device__ __forceinline__ void gn_finalize_group(const float* part, int n, int slots, int C, int g, int cpg, float ns,
-                                                  float eps, float* gstat, int lane) {
+// Group statistics of image `n` from the per-(slot, channel) pairs: ONE warp (all 32 lanes) reduces kG groups at once
+// (g0, g0 + gstep, ...) so that kG x 4 independent L2 loads are in flight per lane — the finaliser sits on the tail of a
+// producer kernel and is pure load latency.  Per group: K = slots * cpg items of `ns` values each, single pass around
+// the pivot item 0; lanes take items lane, lane + 32, ...; lane partials are combined with a fixed shuffle tree.
+template <int kG>
+__device__ __forceinline__ void gn_finalize_groups(const float* part, int n, int slots, int C, int g0, int gstep, int cpg, float ns,
+                                                   float eps, float* gstat, int lane) {
   const float* base = part + (size_t)n * slots * C * 2;
-  const float pivot = ldcg_f2(base + (size_t)(g * cpg) * 2).x;
   const int K = slots * cpg;
-  float s1 = 0.f, s2 = 0.f;
-  for (int i0 = 0; i0 < K; i0 += 128) {          // 4 independent loads in flight per lane
-    float2 e[4];
+  float pivot[kG], s1[kG], s2[kG];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * 32 + lane;
-      if (i < K) {
-        const int sl = i / cpg, c = i - sl * cpg;
-        e[u] = ldcg_f2(base + ((size_t)sl * C + g * cpg + c) * 2);
-      } else {
-        e[u] = make_float2(pivot, 0.f);
+  for (int q = 0; q < kG; ++q) {
+    const int g = g0 + q * gstep;
+    pivot[q] = g < 32 ? ldcg_f2(base + (size_t)(g * cpg) * 2).x : 0.f;
+    s1[q] = 0.f; s2[q] = 0.f;
+  }
+  for (int i0 = 0; i0 < K; i0 += 128) {
+    float2 e[kG][4];
+#pragma unroll
+    for (int q = 0; q < kG; ++q) {
+      const int g = g0 + q * gstep;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        if (g < 32 && i < K) {
+          const int sl = i / cpg, c = i - sl * cpg;
+          e[q][u] = ldcg_f2(base + ((size_t)sl * C + g * cpg + c) * 2);
+        } else {
+          e[q][u] = make_float2(pivot[q], 0.f);
+        }
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float d = e[u].x - pivot;
-      s1 += d;
-      s2 += fmaf(ns * d, d, e[u].y);
-    }
+    for (int q = 0; q < kG; ++q)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float d = e[q][u].x - pivot[q];
+        s1[q] += d;
+        s2[q] += fmaf(ns * d, d, e[q][u].y);
+      }
   }
 #pragma unroll
-  for (int off = 16; off; off >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-  }
-  const float invK = 1.0f / (float)K;
-  const float dm = s1 * invK;                     // group mean - pivot
-  const float mean = pivot + dm;
-  const float m2 = fmaxf(s2 - ns * (float)K * dm * dm, 0.f);
-  const float var = m2 * invK / ns;
-  if (lane == 0) {
-    gstat[((size_t)n * 32 + g) * 2] = mean;
-    gstat[((size_t)n * 32 + g) * 2 + 1] = rsqrtf(var + eps);
+  for (int q = 0; q < kG; ++q) {
+    float a = s1[q], b = s2[q];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, off);
+      b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    const int g = g0 + q * gstep;
+    const float invK = 1.0f / (float)K;
+    const float dm = a * invK;                    // group mean - pivot
+    const float m2 = fmaxf(b - ns * (float)K * dm * dm, 0.f);
+    const float var = m2 * invK / ns;
+    if (lane == 0 && g < 32) {
+      gstat[((size_t)n * 32 + g) * 2] = pivot[q] + dm;
+      gstat[((size_t)n * 32 + g) * 2 + 1] = rsqrtf(var + eps);
+    }
   }
 }
 
 // Arrival protocol, called by ALL `nthreads` threads of a producer's epilogue group (named barrier `bar_id`) AFTER they
 // have written their (mean, M2) pairs for up to kMax (sink, image) pairs.  `img[i] < 0` = nothing delivered for entry i.
 //   add[i]  = channels this CTA delivered for (sink[i], img[i]) in this tile slot
-// The last arriver of an image reduces the image's 32 groups (warp w takes groups w, w + #warps, ...).
+// The last arriver of an image reduces the image's 32 groups (warp w takes groups w, w + #warps, ... four at a time).
 template <int kMax>
 __device__ __forceinline__ void gn_arrive(const GnSink* const (&sink)[kMax], const int (&img)[kMax], const unsigned int (&add)[kMax],
                                           int slots, float ns, int tid, int nthreads, int bar_id, int* s_flag /* [kMax] shared */) {
-  __threadfence();                                // this thread's pairs are visible device-wide before the count moves
-  named_bar_sync(bar_id, nthreads);
+  named_bar_sync(bar_id, nthreads);               // every thread's pair stores happen-before the arrival below
   if (tid < kMax) {
     int last = 0;
     if (sink[tid] != nullptr && img[tid] >= 0 && sink[tid]->gstat != nullptr) {
-      const unsigned int old = atomicAdd(sink[tid]->counter + img[tid], add[tid]);
+      const unsigned int old = atom_add_acq_rel_gpu(sink[tid]->counter + img[tid], add[tid]);
       last = (old + add[tid] == sink[tid]->expected) ? 1 : 0;
     }
     s_flag[tid] = last;
   }
-  named_bar_sync(bar_id, nthreads);
+  named_bar_sync(bar_id, nthreads);               // ... and the acquiring arrival happens-before the finaliser's reads
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
 #pragma unroll
   for (int i = 0; i < kMax; ++i) {
     if (!s_flag[i]) continue;                     // uniform across the group
-    __threadfence();                              // acquire side: the other CTAs' pairs (read with ld.global.cg below)
-    const GnSink& s = *sink[i];
+    const GnSink& s = *sink[i];                   // (pairs are read with ld.global.cg: L2, never a stale L1 line)
     const int cpg = s.cstride / 32;
-    for (int g = warp; g < 32; g += nwarps) gn_finalize_group(s.part, img[i], slots, s.cstride, g, cpg, ns, s.eps, s.gstat, lane);
+    for (int g = warp; g < 32; g += 4 * nwarps) gn_finalize_groups<4>(s.part, img[i], slots, s.cstride, g, nwarps, cpg, ns, s.eps, s.gstat, lane);
   }
   named_bar_sync(bar_id, nthreads);               // s_flag may be rewritten by the next tile
+}
+
+// Deferred arrivals of a persistent producer: instead of one arrival (barrier + GPU-scope atomic round trip + barrier,
+// ~2 us during which the eight epilogue warps idle) per output tile, thread 0 records (sink, image, channels) in a small
+// shared list — merging repeats — and the CTA arrives ONCE for every entry after its last tile.
+constexpr int kGnListCap = 64;
+struct GnArriveList {
+  int cnt;
+  int over;                       // set by thread 0 when the list cannot take another tile's entries: arrive now instead
+  short sink[kGnListCap];
+  short img[kGnListCap];
+  unsigned int add[kGnListCap];
+  int flag[kGnListCap];
+};
+__device__ __forceinline__ void gn_list_add(GnArriveList* L, int d, int img, unsigned int add) {   // thread 0 only
+  for (int j = 0; j < L->cnt; ++j)
+    if (L->sink[j] == d && L->img[j] == img) { L->add[j] += add; return; }
+  const int j = L->cnt++;
+  L->sink[j] = (short)d; L->img[j] = (short)img; L->add[j] = add;
+}
+// all `nthreads` threads of the epilogue group, after the CTA's last tile (every pair store precedes the first barrier)
+__device__ __forceinline__ void gn_list_arrive(GnArriveList* L, const GnSink& s0, const GnSink& s1, int slots, float ns, int tid,
+                                               int nthreads, int bar_id) {
+  named_bar_sync(bar_id, nthreads);
+  const int cnt = L->cnt;
+  for (int j = tid; j < cnt; j += nthreads) {
+    const GnSink& s = L->sink[j] == 0 ? s0 : s1;
+    const unsigned int old = atom_add_acq_rel_gpu(s.counter + L->img[j], L->add[j]);
+    L->flag[j] = (old + L->add[j] == s.expected) ? 1 : 0;
+  }
+  named_bar_sync(bar_id, nthreads);
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  for (int j = 0; j < cnt; ++j) {
+    if (!L->flag[j]) continue;
+    const GnSink& s = L->sink[j] == 0 ? s0 : s1;
+    const int cpg = s.cstride / 32;
+    for (int g = warp; g < 32; g += 4 * nwarps) gn_finalize_groups<4>(s.part, L->img[j], slots, s.cstride, g, nwarps, cpg, ns, s.eps, s.gstat, lane);
+  }
+  named_bar_sync(bar_id, nthreads);
+  if (tid == 0) L->cnt = 0;
 }
 
 // (mean, M2) of the `rows` fp16 values x[r * pitch_h] (r = 0 .. rows-1) read through `ld(r)` -> float2 (two adjacent

@@ -131,6 +131,8 @@ inline int pow2_floor_div(int x, int cap) {   // largest power of two dividing x
 struct ConvDesc {
   View in;                 // input view (for stride 2: the full-resolution input)
   int ksize = 1, stride = 1;
+  int pad_lo = 1;          // stride-2 convs: 1 = symmetric padding 1 (UNet Downsample, reference models/unet.py:99-108);
+                           // 0 = pad (0,1,0,1) then a padding-free conv (VQ-GAN Downsample, ldm/.../model.py:78-87)
   const __half* wt = nullptr;   // [Cout][taps][ipad]
   int ipad = 0;
   const float* bias = nullptr;
@@ -181,7 +183,7 @@ inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn
         const long long units_p = (long long)((m_tiles + cg - 1) / cg) * n_tiles;
         const int workers = cg == 2 ? 74 : 148;
         const int sbytes_p = kConvBM * kConvBK * 2 + (cand / cg) * kConvBK * 2;
-        const size_t extra = (size_t)2 * cand * kConvBM * 2 + (size_t)cand * 40 + 1280;   // two staging buffers, wsum, two bias slots
+        const size_t extra = (size_t)2 * cand * kConvBM * 2 + (size_t)cand * 40 + 1280 + sizeof(GnArriveList);   // two staging buffers, wsum, two bias slots, arrival list
         const int st_p = (int)std::min<size_t>(8, ((size_t)227 * 1024 - extra) / (size_t)sbytes_p);
         // (only layers with at least two PIXEL tiles per worker: that is where the model below was calibrated; getting
         // there through many narrow channel tiles would re-read the A operand once per channel tile)
@@ -305,8 +307,10 @@ inline int conv_finalize(ConvDesc& d) {
   const bool contiguous_tiles = (p.bw == Wout) || (p.bh == 1);
   const bool can_split = d.allow_split && d.partial != nullptr && contiguous_tiles && p.bn <= 2 && d.has_out && !d.out_f32;
   const int want_persist = env_int("RS_CONV_PERSIST", -1);           // 0 / 1 disables / forces the persistent kernel
+  // (the persistent kernel batches its GroupNorm arrivals in a shared list of kGnListCap (sink, image) entries)
   const bool persist_ok = d.has_out && !d.out_f32 && want_persist != 0 && !env_is("RS_CONV_EPI", "direct") &&
-                          !env_is("RS_CONV_IMPL", "simt") && env_int("RS_CONV_MSUB", 0) != 2;
+                          !env_is("RS_CONV_IMPL", "simt") && env_int("RS_CONV_MSUB", 0) != 2 &&
+                          (!(d.sink[0].part || d.sink[1].part) || 2 * N <= kGnListCap);
   const bool can_cluster_split = d.allow_split && contiguous_tiles && p.bn <= 2 && d.has_out && !d.out_f32 && d.Cout % 8 == 0;
   const TileConfig tc = pick_tile_config(m_tiles, cout16, num_kb, d.bn_override ? d.bn_override : env_int("RS_CONV_BN", 0), can_split,
                                          persist_ok && want_persist != 1, can_cluster_split);
@@ -334,8 +338,13 @@ inline int conv_finalize(ConvDesc& d) {
     int t = 0;
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx, ++t) {
-        const int hp = (ky == 1) ? 0 : 1, wp = (kx == 1) ? 0 : 1;
-        p.tap_src[t] = hp * 2 + wp; p.tap_dh[t] = (ky == 0) ? -1 : 0; p.tap_dw[t] = (kx == 0) ? -1 : 0;
+        if (d.pad_lo == 1) {        // input row 2i + ky - 1: parity (ky != 1), one step back for ky = 0
+          const int hp = (ky == 1) ? 0 : 1, wp = (kx == 1) ? 0 : 1;
+          p.tap_src[t] = hp * 2 + wp; p.tap_dh[t] = (ky == 0) ? -1 : 0; p.tap_dw[t] = (kx == 0) ? -1 : 0;
+        } else {                    // input row 2i + ky: parity (ky == 1), one step forward for ky = 2 (TMA zero fill = the pad)
+          const int hp = (ky == 1) ? 1 : 0, wp = (kx == 1) ? 1 : 0;
+          p.tap_src[t] = hp * 2 + wp; p.tap_dh[t] = (ky == 2) ? 1 : 0; p.tap_dw[t] = (kx == 2) ? 1 : 0;
+        }
       }
   }
   // epilogue
@@ -376,7 +385,7 @@ inline int conv_finalize(ConvDesc& d) {
     RS_CHECK(!tc.persist || p.persist, "persistent configuration chosen for an ineligible layer");
     p.num_units = units;
     if (p.persist) {
-      const size_t extra = (size_t)2 * BN * kConvBM * 2 + (size_t)4 * BN * 2 * sizeof(float) + (size_t)2 * BN * sizeof(float) + 256 + 1024;
+      const size_t extra = (size_t)2 * BN * kConvBM * 2 + (size_t)4 * BN * 2 * sizeof(float) + (size_t)2 * BN * sizeof(float) + 256 + 1024 + sizeof(GnArriveList);
       const int st = (int)std::min<size_t>(8, ((size_t)227 * 1024 - extra) / (size_t)stage_bytes);
       RS_CHECK(st >= 2, "persistent conv: shared memory budget");
       p.stages = std::min(st, std::max(2, num_kb));

@@ -57,6 +57,18 @@ def space_timesteps(num_timesteps, sample_timesteps):
     return {int((num_timesteps / sample_timesteps) * x) for x in range(sample_timesteps)}
 
 
+def bicubic_upsample(y, sf):
+    """F.interpolate(y, scale_factor=sf, mode='bicubic') (reference models/gaussian_diffusion.py:503-504) — the library's
+    kernel for fp32 CUDA tensors and integer factors (same A = -0.75 / half-pixel / border-clamp arithmetic as ATen)."""
+    if y.is_cuda and y.dtype == torch.float32 and float(sf).is_integer():
+        yc = y.contiguous()
+        n, c, h, w = yc.shape
+        out = torch.empty(n, c, h * int(sf), w * int(sf), dtype=torch.float32, device=y.device)
+        _lib.check(_lib.lib.rs_op_bicubic_upsample(yc.data_ptr(), n, c, h, w, int(sf), out.data_ptr(), _lib.current_stream()))
+        return out
+    return F.interpolate(y, scale_factor=sf, mode="bicubic")
+
+
 def _tab(arr, t, like):
     """``_extract_into_tensor`` (reference models/gaussian_diffusion.py:92-105): float64 table -> fp32 gather."""
     res = torch.from_numpy(np.asarray(arr)).to(device=t.device)[t].float()
@@ -115,7 +127,7 @@ class ResShiftDiffusion:
         """reference models/gaussian_diffusion.py:500-515 (PyTorch bookend)"""
         data_dtype = y.dtype
         if up_sample and self.sf != 1:
-            y = F.interpolate(y, scale_factor=self.sf, mode="bicubic")
+            y = bicubic_upsample(y, self.sf)
         if first_stage_model is None:
             return y
         model_dtype = next(first_stage_model.parameters()).dtype

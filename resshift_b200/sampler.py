@@ -75,12 +75,31 @@ def load_yaml(path) -> Cfg:
     return Cfg.wrap(resolve(raw))
 
 
+# yaml `target:` strings of the reference that this package implements natively: an unmodified reference config
+# (configs/*.yaml) builds this package's classes; anything else is imported as written
+_NATIVE_TARGETS = {
+    "models.unet.UNetModelSwin": "resshift_b200.models.unet.UNetModelSwin",
+    "models.script_util.create_gaussian_diffusion": "resshift_b200.models.script_util.create_gaussian_diffusion",
+    "ldm.models.autoencoder.VQModelTorch": "resshift_b200.models.autoencoder.VQModelTorch",
+}
+
+
+def _plain(obj):
+    """Cfg / OmegaConf containers -> plain dict / list (constructor kwargs)."""
+    if isinstance(obj, dict) or hasattr(obj, "items"):
+        return {k: _plain(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)) or type(obj).__name__ == "ListConfig":
+        return [_plain(v) for v in obj]
+    return obj
+
+
 def instantiate_from_config(config):
     """reference utils/util_common.py:19-29"""
     if "target" not in config:
         raise KeyError("Expected key `target` to instantiate.")
-    module, cls = config["target"].rsplit(".", 1)
-    return getattr(importlib.import_module(module), cls)(**dict(config.get("params", dict())))
+    target = _NATIVE_TARGETS.get(config["target"], config["target"])
+    module, cls = target.rsplit(".", 1)
+    return getattr(importlib.import_module(module), cls)(**_plain(config.get("params", dict())))
 
 
 def make_configs(ucfg, dcfg, autoencoder: Optional[dict] = None, state_dict: Any = None) -> Cfg:
@@ -119,6 +138,16 @@ def tile_starts(length: int, patch: int, stride: int):
         if s1 not in out:
             out.append(s1)
     return out
+
+
+def plan_tiles(h: int, w: int, patch: int, stride: int, chop_bs: int):
+    """Host-side plan of the tiled pass, identical to iterating the reference's ImageSpliterTh(im, patch, stride, sf,
+    extra_bs=chop_bs) (utils/util_image.py:889-960): (row starts, column starts, tile height, tile width, groups) where
+    `groups` lists, per sample_func call, the (h_start, w_start) of the tiles stacked on the batch axis."""
+    hs_list, ws_list = tile_starts(h, patch, stride), tile_starts(w, patch, stride)
+    starts = [(hs, ws) for hs in hs_list for ws in ws_list]
+    k = max(1, int(chop_bs))
+    return hs_list, ws_list, min(patch, h), min(patch, w), [starts[i:i + k] for i in range(0, len(starts), k)]
 
 
 class BaseSampler:
@@ -230,34 +259,66 @@ class ResShiftSampler(BaseSampler):
         return results.clamp_(-1.0, 1.0)
 
     # ---------------------------------------------------------------------------------------------
-    def _process(self, im_lq, mask=None, noise_repeat=False, mask_back=True):
-        """[b, c, h, w] in [-1, 1] -> [b, c, h*sf, w*sf] in [0, 1]; tiles inputs larger than chop_size
-        (reference sampler.py:176-223 with utils/util_image.py:889-979 ImageSpliterTh semantics:
-        overlapping tiles, per-pixel average of the overlaps)."""
+    def _sample_tiled(self, im_lq, mask=None, noise_repeat=False):
+        """[b, c, h, w] in [-1, 1] -> super-resolved [b, c, h*sf, w*sf] in [-1, 1]; inputs larger than chop_size are cut
+        into overlapping chop_size tiles at the reference's start offsets (utils/util_image.py:923-932), `chop_bs` tiles
+        are stacked on the batch axis per call exactly like ImageSpliterTh.__next__ (:940-960, `extra_bs`) — so the
+        noise drawn per call matches the reference's — and overlaps are averaged (update / gather :962-979) by
+        rs_op_tile_gather in the reference's accumulation order."""
+        from . import _lib
         ctx = torch.autocast("cuda") if self.use_amp else nullcontext()
         b, c, h, w = im_lq.shape
-        if h > self.chop_size or w > self.chop_size:
-            sf, ps, st = self.sf, self.chop_size, self.chop_stride
-            acc = torch.zeros(b, c, h * sf, w * sf, device=im_lq.device)
-            cnt = torch.zeros_like(acc)
-
-            for hs in tile_starts(h, ps, st):
-                for ws in tile_starts(w, ps, st):
-                    he, we = min(hs + ps, h), min(ws + ps, w)
-                    with ctx:
-                        pch = self.sample_func(im_lq[:, :, hs:he, ws:we], noise_repeat=noise_repeat,
-                                               mask=None if mask is None else mask[:, :, hs:he, ws:we])
-                    acc[:, :, hs * sf:he * sf, ws * sf:we * sf] += pch.float()
-                    cnt[:, :, hs * sf:he * sf, ws * sf:we * sf] += 1
-            im_sr = acc / cnt
-        else:
+        if not (h > self.chop_size or w > self.chop_size):
             with ctx:
-                im_sr = self.sample_func(im_lq, noise_repeat=noise_repeat, mask=mask).float()
+                return self.sample_func(im_lq, noise_repeat=noise_repeat, mask=mask).float()
+        sf = self.sf
+        hs_list, ws_list, th, tw, groups = plan_tiles(h, w, self.chop_size, self.chop_stride, self.chop_bs)
+        tiles = []
+        for group in groups:
+            pch = torch.cat([im_lq[:, :, hs:hs + th, ws:ws + tw] for hs, ws in group], dim=0)
+            mch = None if mask is None else torch.cat([mask[:, :, hs:hs + th, ws:ws + tw] for hs, ws in group], dim=0)
+            with ctx:
+                res = self.sample_func(pch, noise_repeat=noise_repeat, mask=mch).float()
+            tiles.extend(torch.split(res, b, dim=0))
+        tiles_t = torch.stack(tiles).contiguous()                                   # [T, b, c, th*sf, tw*sf]
+        out = torch.empty(b, tiles_t.shape[2], h * sf, w * sf, dtype=torch.float32, device=im_lq.device)
+        ys = torch.tensor([v * sf for v in hs_list], dtype=torch.int32, device=im_lq.device)
+        xs = torch.tensor([v * sf for v in ws_list], dtype=torch.int32, device=im_lq.device)
+        _lib.check(_lib.lib.rs_op_tile_gather(tiles_t.data_ptr(), b, tiles_t.shape[2], h * sf, w * sf, th * sf, tw * sf,
+                                              len(hs_list), len(ws_list), ys.data_ptr(), xs.data_ptr(), out.data_ptr(),
+                                              _lib.current_stream()))
+        return out
+
+    def _process(self, im_lq, mask=None, noise_repeat=False, mask_back=True):
+        """[b, c, h, w] in [-1, 1] -> [b, c, h*sf, w*sf] in [0, 1] (reference sampler.py:176-223)."""
+        im_sr = self._sample_tiled(im_lq, mask=mask, noise_repeat=noise_repeat)
         im_sr = im_sr * 0.5 + 0.5
         if mask_back and mask is not None:
             m = mask * 0.5 + 0.5
             im_sr = im_sr * m + (im_lq * 0.5 + 0.5) * (1 - m)
         return im_sr
+
+    def _process_u8(self, lq_u8, mask_u8=None, noise_repeat=False, mask_back=True, bgr=True):
+        """uint8 edges fused on the device: lq_u8 [b, h, w, 3] (RGB) and optional mask_u8 [b, h, w, 1]
+        -> uint8 [b, h*sf, w*sf, 3] in BGR (what cv2.imwrite takes) or RGB order.  Ingest = (v / 255 - 0.5) / 0.5
+        (reference datapipe default transform); emit = clamp, * 0.5 + 0.5, mask-back blend, round(v * 255)
+        (sampler.py:218-223 + utils/util_image.tensor2img :216-273)."""
+        from . import _lib
+        b, h, w, _ = lq_u8.shape
+        lq = torch.empty(b, 3, h, w, dtype=torch.float32, device=lq_u8.device)
+        _lib.check(_lib.lib.rs_op_ingest_u8(lq_u8.contiguous().data_ptr(), b, h, w, 3, lq.data_ptr(), _lib.current_stream()))
+        mask = None
+        if mask_u8 is not None:
+            mask = torch.empty(b, 1, h, w, dtype=torch.float32, device=lq_u8.device)
+            _lib.check(_lib.lib.rs_op_ingest_u8(mask_u8.contiguous().data_ptr(), b, h, w, 1, mask.data_ptr(), _lib.current_stream()))
+        sr = self._sample_tiled(lq, mask=mask, noise_repeat=noise_repeat).contiguous()
+        out = torch.empty(b, h * self.sf, w * self.sf, 3, dtype=torch.uint8, device=lq_u8.device)
+        blend = mask_back and mask is not None
+        if blend and self.sf != 1:
+            raise ValueError("mask-back needs sf == 1 (as in the reference's inpainting tasks)")
+        _lib.check(_lib.lib.rs_op_emit_u8(sr.data_ptr(), lq.data_ptr() if blend else None, mask.data_ptr() if blend else None,
+                                          b, h * self.sf, w * self.sf, int(bgr), out.data_ptr(), _lib.current_stream()))
+        return out
 
     def inference(self, in_path, out_path, mask_path=None, mask_back=True, bs=1, noise_repeat=False):
         """File / folder driver (reference sampler.py:167-308).  Image I/O through OpenCV."""
@@ -274,11 +335,7 @@ class ResShiftSampler(BaseSampler):
             if im is None:
                 raise FileNotFoundError(p)
             im = im[:, :, None] if gray else cv2.cvtColor(im, cv2.COLOR_BGR2RGB)
-            return torch.from_numpy(im.astype(np.float32) / 255.0).permute(2, 0, 1)
-
-        def write(t, p):
-            im = (t.clamp(0, 1) * 255.0).round().byte().permute(1, 2, 0).cpu().numpy()
-            cv2.imwrite(str(p), cv2.cvtColor(im, cv2.COLOR_RGB2BGR))
+            return torch.from_numpy(np.ascontiguousarray(im))                 # uint8 HWC; normalised on the device
 
         exts = {".png", ".jpg", ".jpeg", ".bmp"}
         files = sorted(p for p in in_path.rglob("*") if p.suffix.lower() in exts) if in_path.is_dir() else [in_path]
@@ -294,10 +351,9 @@ class ResShiftSampler(BaseSampler):
                 if mask_path is not None:
                     mp = Path(mask_path)
                     mask = torch.stack([read(mp / p.name if mp.is_dir() else mp, gray=True) for p in paths]).cuda()
-                    mask = (mask - 0.5) / 0.5
-                sr = self._process((lq - 0.5) / 0.5, mask=mask, noise_repeat=noise_repeat, mask_back=mask_back)
+                sr = self._process_u8(lq, mask_u8=mask, noise_repeat=noise_repeat, mask_back=mask_back, bgr=True).cpu().numpy()
                 for p, im in zip(paths, sr):
-                    write(im, out_path / f"{p.stem}.png")
+                    cv2.imwrite(str(out_path / f"{p.stem}.png"), im)
             if self.num_gpus > 1:
                 dist.barrier()
         self.write_log(f"Processing done, enjoy the results in {out_path}")

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
 S=r2_s1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${S}_smi.txt 2>&1
-timeout 1800 python -m pytest tests -m gpu -q -rA -x --timeout=600 2>&1 | tail -150 > $O/${S}_pytest.log
+timeout 1800 python -m pytest tests -m gpu -q -rA --timeout=600 2>&1 | tail -150 > $O/${S}_pytest.log
 timeout 300 python bench.py --quick --steps 5 > $O/${S}_quick_default.log 2>$O/${S}_quick_default.err
 RS_CONV_TAILSKIP=0 timeout 300 python bench.py --quick --steps 5 > $O/${S}_quick_notailskip.log 2>/dev/null
 RS_MLP_NORM_FUSE=0 timeout 300 python bench.py --quick --steps 5 > $O/${S}_quick_nomlpnorm.log 2>/dev/null

@@ -171,38 +171,38 @@ def test_tile_starts_match_reference_image_splitter():
             del sys.modules[m]
 
 
-def test_tiled_processing_matches_reference_splitter_average():
-    """ResShiftSampler._process on an input larger than chop_size (host-side tiling + overlap average) against the
-    reference's ImageSpliterTh loop (sampler.py:189-206) with the same stand-in per-tile function."""
+def test_tile_plan_matches_reference_splitter():
+    """Host side of the tiled pass: plan_tiles must enumerate exactly the tiles, in exactly the batches, that iterating
+    the reference's ImageSpliterTh(extra_bs=chop_bs) yields (utils/util_image.py:889-960) — the per-call batch shape fixes
+    the noise draw, the order fixes the overlap-average's summation order.  (The device side — rs_op_tile_gather against
+    the reference-form accumulate — is tests/test_gpu_vq.py::test_image_edges_match_torch and the tiled GPU test.)"""
     import sys
-    import torch.nn.functional as F
-    from resshift_b200.sampler import ResShiftSampler
+    from resshift_b200.sampler import plan_tiles
     ref_root = Path("/root/reference")
     if not ref_root.exists():
         pytest.skip("reference tree not present")
-    s = object.__new__(ResShiftSampler)                     # no model build: only the tiling logic is exercised
-    s.sf, s.chop_size, s.chop_stride, s.use_amp = 4, 32, 28, False
-
-    def fake(y0, noise_repeat=False, mask=None):            # position-dependent so that overlaps really get averaged
-        up = F.interpolate(y0, scale_factor=4, mode="nearest")
-        ramp = torch.linspace(0, 1, up.shape[-1]).view(1, 1, 1, -1)
-        return (up * 0.5 + 0.25 * ramp).clamp(-1, 1)
-    s.sample_func = fake
-    g = torch.Generator().manual_seed(3)
-    im = torch.rand(2, 3, 75, 50, generator=g) * 2 - 1
-    got = s._process(im, mask=None, noise_repeat=False, mask_back=True)
     sys.path[:0] = [str(ROOT / "oracle" / "_shims"), str(ref_root)]
     try:
         from utils.util_image import ImageSpliterTh
-        sp = ImageSpliterTh(im, 32, 28, sf=4, extra_bs=1)
-        for pch, idx in sp:
-            sp.update(fake(pch), idx)
-        want = sp.gather() * 0.5 + 0.5
+        for (h, w, ps, st, sf, bs) in [(75, 50, 32, 28, 4, 1), (148, 112, 128, 112, 4, 3), (64, 200, 64, 48, 4, 8),
+                                       (40, 40, 64, 48, 4, 2), (592 // 4, 448 // 4, 128, 112, 4, 4), (512, 700, 256, 224, 1, 5)]:
+            im = torch.zeros(2, 3, h, w)
+            sp = ImageSpliterTh(im, ps, st, sf=sf, extra_bs=bs)
+            ref_groups, ref_shapes = [], []
+            for pch, idx in sp:                           # (index_infos' ends may exceed the image; the slice clips them)
+                ref_groups.append([(i[0] // sf, i[2] // sf) for i in idx])
+                ref_shapes.append((pch.shape[0], pch.shape[2], pch.shape[3]))
+            hs_list, ws_list, th, tw, groups = plan_tiles(h, w, ps, st, bs)
+            if h <= ps and w <= ps:                       # the reference does not tile at all in this case (sampler.py:186)
+                assert groups == [[(0, 0)]]
+                continue
+            assert groups == ref_groups, (h, w, ps, st, bs)
+            assert [(2 * len(g), th, tw) for g in groups] == ref_shapes, (h, w, ps, st, bs)
+            assert hs_list == sp.height_starts_list and ws_list == sp.width_starts_list
     finally:
         del sys.path[:2]
         for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
             del sys.modules[m]
-    assert got.shape == want.shape and torch.allclose(got, want, atol=1e-6)
 
 
 def test_overlay_resolves_reference_module_names_to_this_package(tmp_path):
