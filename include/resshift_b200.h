@@ -193,6 +193,10 @@ long long rs_op_groupnorm_scratch_floats(int N, int H, int W, int C);
 int rs_op_groupnorm_apply(const void* x, int N, int H, int W, int C, int ld, const float* gamma, const float* beta,
                           const float* film, long long film_sN, int silu, void* y, int y_ld, const float* gstat,
                           void* stream);
+/* ... or on the producers' raw (mean, M2) pairs part[N][slots][C][2]: the consumer combines them itself */
+int rs_op_groupnorm_apply_pairs(const void* x, int N, int H, int W, int C, int ld, const float* gamma, const float* beta,
+                                const float* film, long long film_sN, int silu, void* y, int y_ld, const float* part,
+                                int slots, void* stream);
 /* window attention core (reference models/swin_transformer.py:114-145,251-275); qkv [N,H,W,3*heads*32] */
 int rs_op_expand_relpos(const float* table_225xh, float* dense_hx64x64, int heads, void* stream);
 int rs_op_window_attention(const void* qkv, int N, int H, int W, int heads, int shift, const float* bias_dense,

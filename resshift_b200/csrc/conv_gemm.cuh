@@ -389,6 +389,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
             q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
           }
           *a0 = o0; *a1 = o1;
+          // statistics of the values as stored, while the tile drains (gn_stats.cuh)
+          if (want_stats) warp_chunk_stats(o0, o1, lane, wsum_all + ((size_t)(sub * 4 + quad) * p.BN + c) * 2);
         }
       }
       fence_proxy_async_smem();
@@ -405,23 +407,22 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
         tma_store_commit();
       }
       if (want_stats) {
-        // column statistics of the staged (fp16-rounded) tile, read back from shared memory while the TMA store drains
-        float* wstat = wsum_all;                                     // [2 halves][BN][2]
-        int* s_flag = reinterpret_cast<int*>(wstat + 4 * p.BN);
+        int* s_flag = reinterpret_cast<int*>(wsum_all + (size_t)p.msub * 8 * p.BN);
         for (int sub = 0; sub < p.msub; ++sub) {
           int tw, th, w0, h0, n0;
           tile_origin(sub, tw, th, w0, h0, n0);
-          staged_tile_column_stats(smem + (size_t)sub * sub_bytes, p.BN, bc, etid, wstat);
-          named_bar_sync(1, 32 * kConvEpiWarps);
           const int ncols = min(p.BN, p.Cout - col0);
           const int slot = th * p.tiles_w + tw;
           if (n0 < p.Nimg)                                           // (else: padding tile of an odd pair)
-            write_tile_pairs(wstat, p.BN, ncols, col0, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kConvEpiWarps);
-          const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
-          const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
-          const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
-          const unsigned int ad[4] = {(unsigned)ncols, (unsigned)ncols, (unsigned)ncols, (unsigned)ncols};
-          gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kConvEpiWarps, 1, s_flag);
+            write_quad_pairs(wsum_all + (size_t)sub * 8 * p.BN, p.BN, ncols, col0, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1],
+                             etid, 32 * kConvEpiWarps);
+          if (p.sink[0].gstat || p.sink[1].gstat) {                  // producer-side finalisation (large tensors only)
+            const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
+            const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
+            const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
+            const unsigned int ad[4] = {(unsigned)ncols, (unsigned)ncols, (unsigned)ncols, (unsigned)ncols};
+            gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kConvEpiWarps, 1, s_flag);
+          }
         }
       }
       if (etid == 0) tma_store_wait_read();
@@ -549,12 +550,14 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_gemm_sm100_kernel(const 
           const int ncols = max(0, min(cw, p.Cout - (col0 + cbase)));
           if (n0 < p.Nimg)
             write_tile_pairs(s_col, cw, ncols, col0 + cbase, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kConvEpiWarps);
-          int* s_flag = reinterpret_cast<int*>(s_col + 4 * cw);
-          const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
-          const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
-          const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
-          const unsigned int ad[4] = {(unsigned)ncols, (unsigned)ncols, (unsigned)ncols, (unsigned)ncols};
-          gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kConvEpiWarps, 1, s_flag);
+          if (p.sink[0].gstat || p.sink[1].gstat) {
+            int* s_flag = reinterpret_cast<int*>(s_col + 4 * cw);
+            const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
+            const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
+            const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
+            const unsigned int ad[4] = {(unsigned)ncols, (unsigned)ncols, (unsigned)ncols, (unsigned)ncols};
+            gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kConvEpiWarps, 1, s_flag);
+          }
         }
       }
     }

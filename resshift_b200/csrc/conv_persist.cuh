@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
           q1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
         }
         *a0 = o0; *a1 = o1;
+        // statistics of the values as stored, while the tile drains (gn_stats.cuh)
+        if (want_stats) warp_chunk_stats(o0, o1, lane, wsum + ((size_t)quad * p.BN + c) * 2);
       }
       // this warp has read its share of the accumulator: hand the buffer back to the MMA issuer (tile i + 2)
       tc_fence_before();
@@ -268,27 +270,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_persist_sm100_kerne
           if (col0 + bq * bc < p.Cout) tma_store_4d(&p.tmOut, s_stage + (size_t)bq * blk_bytes, col0 + bq * bc, w0, h0, n0);
         tma_store_commit();
       }
-      if (want_stats) {
-        // column statistics of the staged (fp16-rounded) tile, read back from shared memory while its TMA store drains
-        float* wstat = wsum;                                         // [2 halves][BN][2]
-        staged_tile_column_stats(s_stage, p.BN, bc, etid, wstat);
-        named_bar_sync(1, 32 * kConvEpiWarps);
+      if (want_stats && n0 < p.Nimg) {                               // (else: padding tile of an odd pair)
         const int ncols = min(p.BN, p.Cout - col0);
         const int slot = th * p.tiles_w + tw;
-        if (n0 < p.Nimg) {                                           // (else: padding tile of an odd pair)
-          write_tile_pairs(wstat, p.BN, ncols, col0, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kConvEpiWarps);
-          if (etid == 0) {                                           // arrivals are batched: one round after the last tile
+        write_quad_pairs(wsum, p.BN, ncols, col0, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kConvEpiWarps);
+        if (etid == 0) {                                             // producer-side finalisation: arrivals are batched
 #pragma unroll
-            for (int d = 0; d < 2; ++d)
-              if (p.sink[d].part && p.sink[d].gstat) {
-                gn_list_add(alist, d, n0, (unsigned)ncols);
-                if (p.bn == 2 && n0 + 1 < p.Nimg) gn_list_add(alist, d, n0 + 1, (unsigned)ncols);
-              }
-          }
+          for (int d = 0; d < 2; ++d)
+            if (p.sink[d].part && p.sink[d].gstat) {
+              gn_list_add(alist, d, n0, (unsigned)ncols);
+              if (p.bn == 2 && n0 + 1 < p.Nimg) gn_list_add(alist, d, n0 + 1, (unsigned)ncols);
+            }
         }
       }
     }
-    if (want_stats) gn_list_arrive(alist, p.sink[0], p.sink[1], p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kConvEpiWarps, 1);
+    if (want_stats && (p.sink[0].gstat || p.sink[1].gstat)) gn_list_arrive(alist, p.sink[0], p.sink[1], p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kConvEpiWarps, 1);
     if (etid == 0) tma_store_wait_read();
   }
 

@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const __grid_constan
         dst[0] = mean; dst[1] = m2;
       }
   }
+  if (!(p.sink[0].gstat || p.sink[1].gstat)) return;
   int* s_flag = reinterpret_cast<int*>(s_red + (size_t)lanes * ccols * 3);
   const GnSink* const sk[2] = {&p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr};
   const int im[2] = {n, n};

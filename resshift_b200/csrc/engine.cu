@@ -257,7 +257,7 @@ int build_inventory(rs_engine& e) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-enum OpKind { OP_CONV, OP_GN, OP_ATTN, OP_UPSAMPLE, OP_MLP, OP_SOFTMAX };
+enum OpKind { OP_CONV, OP_GN, OP_ATTN, OP_UPSAMPLE, OP_MLP, OP_SOFTMAX, OP_FORK, OP_JOIN };
 
 struct Tensor {
   size_t bytes = 0;
@@ -288,7 +288,8 @@ struct Op {
   int gn_index = -1;                    // GroupNorm: index of its [N][32][2] group statistics / [N] arrival counters
   bool to_f32 = false;                  // conv: writes the fp32 NCHW model output
   int split_tens = -1;                  // conv: workspace tensor holding split-K partial sums (or -1)
-  struct StatDst { int list; int op; int coff; };
+  int stream = 0;                       // 0: the caller's stream; k > 0: side stream k of the plan (concurrent batch slices)
+  struct StatDst { int list; int op; int coff; int img_off; };
   std::vector<StatDst> stat_dst;        // conv: GroupNorm ops whose statistics this conv's epilogue produces
 };
 
@@ -313,6 +314,18 @@ struct rs_plan {
   float* out_f32 = nullptr;  // model output (fp32 NCHW), inside the state region
   bool bound = false;
   int launches = 0;
+  // Low-resolution levels (a handful of output tiles per layer at batch 16: every kernel is latency-bound and leaves most
+  // SMs idle) run as `branches` independent batch slices on concurrent streams; each slice's kernels depend only on its
+  // own predecessors, so two (or four) of these small kernels share the machine.  Streams / events belong to the plan;
+  // fork / join are event edges, so the structure is captured into the sampler's CUDA graph as parallel branches.
+  int branches = 1;
+  std::vector<cudaStream_t> side;          // branches - 1 side streams
+  std::vector<cudaEvent_t> ev;             // [0] fork, [k] join of side stream k
+  std::vector<std::pair<int, int>> sections;   // [first, last] global op index of every concurrent section
+  ~rs_plan() {
+    for (cudaStream_t s : side) cudaStreamDestroy(s);
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
   int vq_which = -1;         // -1: denoiser plan; 0 / 1: VQ-GAN encode / decode plan (vq.inc)
   int imgH = 0, imgW = 0;    // VQ plans: image size (H, W above are the latent size)
   // The schedule tables and the FiLM table live in this plan's workspace and are shared by rs_plan_forward (FiLM rows
@@ -332,7 +345,10 @@ struct rs_plan {
     return v;
   }
   static View slice(const View& base, int c0, int C) {
-    View v = base; v.off = base.off + c0; v.C = C; return v;
+    View v = base; v.off = base.off + c0; v.c0 = base.c0 + c0; v.C = C; return v;
+  }
+  static View batch(const View& base, int n0, int n) {       // images [n0, n0 + n) of the view
+    View v = base; v.off = base.off + (long long)n0 * base.sN(); v.n0 = base.n0 + n0; v.N = n; return v;
   }
   void touch(const View& v, int opi) {
     if (v.tens < 0) return;
@@ -349,14 +365,42 @@ struct Builder {
   std::vector<Op>* cur;
   size_t stats_off = 0;
   int n_gn = 0;
-  struct Writer { long long off; int C; int list; int op; };
-  std::map<int, std::vector<Writer>> writers;      // tensor id -> latest conv writers by channel range
+  struct Writer { int c0; int C; int n0; int N; int list; int op; };
+  std::map<int, std::vector<Writer>> writers;      // tensor id -> latest writers by (channel range, image range)
+  int cur_stream = 0;                              // ops are tagged with the stream of the batch slice being built
+  static bool overlaps(const Writer& w, const View& v, int C) {
+    return w.c0 < v.c0 + C && v.c0 < w.c0 + w.C && w.n0 < v.n0 + v.N && v.n0 < w.n0 + w.N;
+  }
+  static bool inside(const Writer& w, const View& v) {
+    return w.c0 >= v.c0 && w.c0 + w.C <= v.c0 + v.C && w.n0 >= v.n0 && w.n0 + w.N <= v.n0 + v.N;
+  }
+  void note_writer(const View& out, int C) {
+    auto& ws = writers[out.tens];
+    ws.erase(std::remove_if(ws.begin(), ws.end(), [&](const Writer& w) { return overlaps(w, out, C); }), ws.end());
+    ws.push_back({out.c0, C, out.n0, out.N, list_id(), (int)cur->size() - 1});
+  }
+  // producers of every (channel, image) of `in` whose epilogues can deliver GroupNorm statistics (empty: not fusable)
+  std::vector<Writer> covering_writers(const View& in) {
+    bool fusable = false;
+    conv_tile_slots(in.H, in.W, &fusable);
+    std::vector<Writer> prod;
+    if (fuse_stats && fusable) {
+      long long covered = 0;
+      auto it = writers.find(in.tens);
+      if (it != writers.end())
+        for (const Writer& w : it->second)
+          if (inside(w, in)) { prod.push_back(w); covered += (long long)w.C * w.N; }
+      bool ok = covered == (long long)in.C * in.N;
+      for (const Writer& w : prod) ok = ok && list(w.list)[w.op].stat_dst.size() < 2;
+      if (!ok) prod.clear();
+    }
+    return prod;
+  }
   const bool fuse_mlp = env_int("RS_MLP_FUSE", 1) && !env_is("RS_CONV_IMPL", "simt");
-  // norm2 applied inside the fused MLP kernel (bit-identical to the separate pass).  Round 1 kept it off because every MLP
-  // CTA re-derived the affine from slots x C partial sums; with the group statistics finalised by the producer's last CTA
-  // (gn_stats.cuh) the preamble is one 256-byte read per image, so it is ON: one launch and one activation round trip
-  // less per Swin block (RS_MLP_NORM_FUSE=0 restores the separate gn_apply launch)
-  const bool fuse_mlp_norm = env_int("RS_MLP_NORM_FUSE", 1) != 0;
+  // norm2 applied inside the fused MLP kernel (bit-identical to the separate pass): implemented, measured twice — with
+  // every MLP CTA combining the statistics itself (round 1) and with producer-finalised statistics (profiles/r2_s2:
+  // 4.73 vs 4.69 ms per step) — and not faster either way, so it stays OFF (RS_MLP_NORM_FUSE=1 enables it)
+  const bool fuse_mlp_norm = env_int("RS_MLP_NORM_FUSE", 0) != 0;
   const bool fuse_stats = env_int("RS_GN_FUSE", 1) && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt");
   Builder(rs_plan& p) : P(p), E(*p.e), cur(&p.ops) {}
   int list_id() const { return cur == &P.fe_ops ? 0 : 1; }
@@ -385,32 +429,19 @@ struct Builder {
     }
     const int i = opi();
     P.touch(in, i); if (out) P.touch(*out, i); if (res) P.touch(*res, i);
+    op.stream = cur_stream;
     cur->push_back(op);
-    if (out && !out_f32 && out->tens >= 0) {          // remember the latest writer of this channel range
-      auto& ws = writers[out->tens];
-      ws.erase(std::remove_if(ws.begin(), ws.end(), [&](const Writer& w) {
-                 return w.off < out->off + cout && out->off < w.off + w.C; }), ws.end());
-      ws.push_back({out->off, cout, list_id(), (int)cur->size() - 1});
-    }
+    if (out && !out_f32 && out->tens >= 0) note_writer(*out, cout);   // the latest writer of this (channel, image) range
   }
   void gn(const View& in, const std::string& name, const View& out, int silu, int film_off, float eps = 1e-5f) {
     Op op; op.kind = OP_GN;
     op.gn.in = in; op.gn.out = out; op.gn.silu = silu; op.gn.film_off = film_off; op.gn.eps = eps;
+    op.gn.film_n0 = in.n0;
     op.g_name = name;
-    // can the producers' epilogues deliver the statistics?  (every channel of the view written by a conv of this plan)
-    bool fusable = false;
-    const int tile_slots = conv_tile_slots(in.H, in.W, &fusable);
-    std::vector<Writer> prod;
-    if (fuse_stats && fusable) {
-      int covered = 0;
-      auto it = writers.find(in.tens);
-      if (it != writers.end())
-        for (const Writer& w : it->second)
-          if (w.off >= in.off && w.off + w.C <= in.off + in.C) { prod.push_back(w); covered += w.C; }
-      bool ok = covered == in.C;
-      for (const Writer& w : prod) ok = ok && list(w.list)[w.op].stat_dst.size() < 2;
-      if (!ok) prod.clear();
-    }
+    // can the producers' epilogues deliver the statistics?  (every channel of every image of the view written by a
+    // conv / MLP of this plan)
+    const int tile_slots = conv_tile_slots(in.H, in.W);
+    std::vector<Writer> prod = covering_writers(in);
     int chunks, rows;
     gn_chunks(in.H * in.W, in.N, &chunks, &rows);
     op.gn.fused = !prod.empty();
@@ -420,33 +451,18 @@ struct Builder {
     stats_off += align_up((size_t)in.N * op.gn.slots * in.C * 2 * sizeof(float), 256);
     const int i = opi();
     P.touch(in, i); P.touch(out, i);
+    op.stream = cur_stream;
     cur->push_back(op);
     for (const Writer& w : prod)
-      list(w.list)[w.op].stat_dst.push_back({list_id(), (int)cur->size() - 1, (int)(w.off - in.off)});
+      list(w.list)[w.op].stat_dst.push_back({list_id(), (int)cur->size() - 1, w.c0 - in.c0, w.n0 - in.n0});
   }
   void attn(const View& qkv, const View& out, const std::string& blk, int shift) {
     Op op; op.kind = OP_ATTN; op.a_in = qkv; op.a_out = out; op.a_shift = shift;
     op.w_name = blk + ".attn.relative_position_bias_table";
     const int i = opi();
     P.touch(qkv, i); P.touch(out, i);
+    op.stream = cur_stream;
     cur->push_back(op);
-  }
-  // producers of every channel of `in` whose epilogues can deliver GroupNorm statistics (empty: not fusable)
-  std::vector<Writer> stat_producers(const View& in) {
-    bool fusable = false;
-    conv_tile_slots(in.H, in.W, &fusable);
-    std::vector<Writer> prod;
-    if (fuse_stats && fusable) {
-      int covered = 0;
-      auto it = writers.find(in.tens);
-      if (it != writers.end())
-        for (const Writer& w : it->second)
-          if (w.off >= in.off && w.off + w.C <= in.off + in.C) { prod.push_back(w); covered += w.C; }
-      bool ok = covered == in.C;
-      for (const Writer& w : prod) ok = ok && list(w.list)[w.op].stat_dst.size() < 2;
-      if (!ok) prod.clear();
-    }
-    return prod;
   }
   // norm_name non-empty: `in` is the un-normalised tensor and the kernel applies that GroupNorm to its X tile itself
   // (returns false, adding nothing, when the statistics cannot come from the producers' epilogues)
@@ -458,7 +474,7 @@ struct Builder {
     op.w2_name = name + ".fc2.weight"; op.b2_name = name + ".fc2.bias";
     std::vector<Writer> prod;
     if (!norm_name.empty()) {
-      prod = stat_producers(in);
+      prod = covering_writers(in);
       if (prod.empty() || Hd < 4 * E) return false;
       op.g_name = norm_name;
       op.gn.in = in; op.gn.fused = true; op.gn.slots = conv_tile_slots(in.H, in.W);
@@ -468,23 +484,21 @@ struct Builder {
     }
     const int i = opi();
     P.touch(in, i); P.touch(out, i); P.touch(res, i);
+    op.stream = cur_stream;
     cur->push_back(op);
     for (const Writer& w : prod)
-      list(w.list)[w.op].stat_dst.push_back({list_id(), (int)cur->size() - 1, (int)(w.off - in.off)});
-    if (out.tens >= 0) {
-      auto& ws = writers[out.tens];
-      ws.erase(std::remove_if(ws.begin(), ws.end(), [&](const Writer& w) {
-                 return w.off < out.off + E && out.off < w.off + w.C; }), ws.end());
-      ws.push_back({out.off, E, list_id(), (int)cur->size() - 1});
-    }
+      list(w.list)[w.op].stat_dst.push_back({list_id(), (int)cur->size() - 1, w.c0 - in.c0, w.n0 - in.n0});
+    if (out.tens >= 0) note_writer(out, E);
     return true;
   }
   void upsample(const View& in, const View& out) {
     Op op; op.kind = OP_UPSAMPLE; op.u_in = in; op.u_out = out;
     const int i = opi();
     P.touch(in, i); P.touch(out, i);
+    op.stream = cur_stream;
     cur->push_back(op);
   }
+  void marker(OpKind k) { Op op; op.kind = k; cur->push_back(op); }
 
   // ResBlock (reference models/unet.py:186-206)
   void res_block(const View& x, const std::string& p, int cout, const View& out) {
@@ -594,6 +608,14 @@ int finish_layout(rs_plan& P, Builder& b, size_t state_bytes, bool unet) {
   P.off_state = region(2 * align_up(lat, 256));
   // persistent tensors first, then liveness-packed temporaries (RS_NO_REUSE=1 keeps every tensor
   // alive for the whole forward so that rs_plan_probe can read any block output afterwards)
+  // tensors born or last used inside a concurrent section stay allocated for the whole section: its batch slices run
+  // on different streams, so "op index order" no longer implies "executed before"
+  for (const auto& sec : P.sections)
+    for (Tensor& tz : P.tensors) {
+      if (tz.last < 0) continue;
+      if (tz.first >= sec.first && tz.first <= sec.second) tz.first = sec.first;
+      if (tz.last >= sec.first && tz.last <= sec.second) tz.last = sec.second;
+    }
   if (env_int("RS_NO_REUSE", 0)) for (Tensor& tz : P.tensors) tz.persistent = true;
   for (Tensor& tz : P.tensors) if (tz.persistent) tz.off = region(tz.bytes);
   P.off_temps = off;
@@ -674,6 +696,44 @@ int build_plan(rs_plan& P) {
     const int ctot = topo.output_blocks[j][0].a;       // ch + ich
     cat[j] = P.make_view(B, in_h[k], in_w[k], ctot);
   }
+  // ---- concurrent batch slices for the few-tile levels (see rs_plan::branches) --------------------------------
+  {
+    int nb = env_int("RS_LOWRES_STREAMS", 2);
+    if (nb < 1) nb = 1;
+    while (nb > 1 && (B % nb != 0 || B / nb < 1)) --nb;
+    P.branches = nb;
+  }
+  const long long low_tiles = env_int("RS_LOWRES_TILES", 64);       // a level is "few-tile" when batch * H * W / 128 <= this
+  auto is_low = [&](int hh, int ww) { return (long long)B * hh * ww / 128 <= low_tiles; };
+  bool in_sec = false;
+  int sec_first = 0;
+  auto leave = [&]() {
+    if (!in_sec) return;
+    const int last = b.opi() - 1;
+    b.marker(OP_JOIN);
+    P.sections.push_back({sec_first, last});
+    in_sec = false;
+  };
+  // one block of the topology: as a whole, or as `branches` batch slices on their own streams
+  auto run = [&](const View& hin, const std::string& prefix, const std::vector<Layer>& layers, const View& dest, View* hout) -> int {
+    bool low = P.branches > 1 && is_low(hin.H, hin.W);
+    if (P.branches > 1 && !low && layers.size() == 1 && layers[0].kind == 3) low = is_low(hin.H / 2, hin.W / 2);   // the stride-2 conv entering the section
+    if (!low) {
+      leave();
+      return b.run_block(hin, prefix, layers, dest, hout);
+    }
+    if (!in_sec) { b.marker(OP_FORK); sec_first = b.opi(); in_sec = true; }
+    const int per = B / P.branches;
+    for (int k = 0; k < P.branches; ++k) {
+      View tmp;
+      b.cur_stream = k;
+      int rc = b.run_block(rs_plan::batch(hin, k * per, per), prefix, layers, rs_plan::batch(dest, k * per, per), &tmp);
+      b.cur_stream = 0;
+      if (rc) return rc;
+    }
+    *hout = dest;
+    return 0;
+  };
   // encoder
   View h = P.xin;
   for (int i = 0; i < n_in; ++i) {
@@ -682,14 +742,14 @@ int build_plan(rs_plan& P) {
     View dest = rs_plan::slice(cat[j], cat[j].C - ich, ich);
     // the input view of the first conv must expose the padded channel count (weights are zero-padded)
     View hin = h;
-    int rc = b.run_block(hin, "input_blocks." + std::to_string(i), topo.input_blocks[i], dest, &h);
+    int rc = run(hin, "input_blocks." + std::to_string(i), topo.input_blocks[i], dest, &h);
     if (rc) return rc;
     P.block_out["input_blocks." + std::to_string(i)] = h;
   }
   // middle: writes into the h-slice of cat[0]
   {
     View dest = rs_plan::slice(cat[0], 0, cat[0].C - topo.in_block_ch[n_in - 1]);
-    int rc = b.run_block(h, "middle_block", topo.middle, dest, &h); if (rc) return rc;
+    int rc = run(h, "middle_block", topo.middle, dest, &h); if (rc) return rc;
     P.block_out["middle_block"] = h;
   }
   // decoder
@@ -703,11 +763,12 @@ int build_plan(rs_plan& P) {
       const Layer& L0 = topo.output_blocks[j][0];
       dest = P.make_view(B, cat[j].H, cat[j].W, L0.b);
     }
-    int rc = b.run_block(cat[j], "output_blocks." + std::to_string(j), topo.output_blocks[j], dest, &h);
+    int rc = run(cat[j], "output_blocks." + std::to_string(j), topo.output_blocks[j], dest, &h);
     if (rc) return rc;
     P.block_out["output_blocks." + std::to_string(j)] = h;
     final_h = h;
   }
+  leave();
   // head (reference models/unet.py:859-863,894)
   View t = P.make_view(B, final_h.H, final_h.W, final_h.C);
   b.gn(final_h, "out.0", t, 1, -1);
@@ -721,11 +782,22 @@ void resolve(rs_plan& P, View& v) {
 }
 
 // statistics destination of a producer: the consuming GroupNorm's pair buffer / group statistics / arrival counters
-GnSink make_sink(rs_plan& P, const Op& g, int coff) {
+// (img_off: a producer that covers only images [img_off, ...) of the consumer — a batch slice on a side stream)
+// Producer-side finalisation (the last producer CTA of an image writes gstat) only pays for tensors with many tile slots
+// (the VQ-GAN's 128x128 / 256x256 maps: every consumer CTA would otherwise re-read slots x C pairs); on the denoiser's
+// small maps the arrival + reduction on the producer's tail costs more than it saves (profiles/r2_s1, r2_s2), so there
+// the consumers combine the pairs themselves.  RS_GN_FINALIZE_SLOTS moves the threshold.
+bool gn_finalizes(const Op& g) {
+  static const int thr = env_int("RS_GN_FINALIZE_SLOTS", 64);
+  return g.gn.slots > thr;
+}
+GnSink make_sink(rs_plan& P, const Op& g, int coff, int img_off = 0) {
   GnSink s{};
-  s.part = reinterpret_cast<float*>(P.ws + P.off_stats + g.stats_off);
-  s.gstat = reinterpret_cast<float*>(P.ws + P.off_gstat) + (size_t)g.gn_index * P.B * 64;
-  s.counter = reinterpret_cast<unsigned int*>(P.ws + P.off_counters) + (size_t)g.gn_index * P.B;
+  s.part = reinterpret_cast<float*>(P.ws + P.off_stats + g.stats_off) + (size_t)img_off * g.gn.slots * g.gn.in.C * 2;
+  if (gn_finalizes(g)) {
+    s.gstat = reinterpret_cast<float*>(P.ws + P.off_gstat) + (size_t)g.gn_index * P.B * 64 + (size_t)img_off * 64;
+    s.counter = reinterpret_cast<unsigned int*>(P.ws + P.off_counters) + (size_t)g.gn_index * P.B + img_off;
+  }
   s.cstride = g.gn.in.C; s.coff = coff; s.expected = (unsigned)(g.gn.slots * g.gn.in.C); s.eps = g.gn.eps;
   return s;
 }
@@ -738,7 +810,7 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
         op.conv.sink[i] = GnSink{};
         if (i < (int)op.stat_dst.size()) {
           const Op::StatDst& sd = op.stat_dst[i];
-          op.conv.sink[i] = make_sink(P, (sd.list == 0 ? P.fe_ops : P.ops)[sd.op], sd.coff);
+          op.conv.sink[i] = make_sink(P, (sd.list == 0 ? P.fe_ops : P.ops)[sd.op], sd.coff, sd.img_off);
         }
       }
       ConvDesc& d = op.conv;
@@ -782,7 +854,8 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       const Param* w1p = E.find(op.w_name); const Param* w2p = E.find(op.w2_name);
       RS_CHECK(w1p->ipad == m.E && w2p->ipad == m.Hd, "MLP weight padding");
       if (!op.g_name.empty()) {
-        m.gn_in_gstat = make_sink(P, op, 0).gstat;
+        const GnSink sk = make_sink(P, op, 0);
+        m.gn_in_gstat = sk.gstat; m.gn_in_part = sk.part; m.gn_in_slots = op.gn.slots;
         m.gn_in_gamma = E.at<float>(op.g_name + ".weight"); m.gn_in_beta = E.at<float>(op.g_name + ".bias");
         RS_CHECK(m.gn_in_gamma && m.gn_in_beta, "missing GroupNorm parameters " + op.g_name);
       }
@@ -790,7 +863,7 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
         m.sink[i] = GnSink{};
         if (i < (int)op.stat_dst.size()) {
           const Op::StatDst& sd = op.stat_dst[i];
-          m.sink[i] = make_sink(P, (sd.list == 0 ? P.fe_ops : P.ops)[sd.op], sd.coff);
+          m.sink[i] = make_sink(P, (sd.list == 0 ? P.fe_ops : P.ops)[sd.op], sd.coff, sd.img_off);
         }
       }
       int rc = mlp_finalize(m); if (rc) return rc;
@@ -800,6 +873,8 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       op.a_bias = E.at<float>(op.w_name);
       RS_CHECK(op.a_bias != nullptr, "missing " + op.w_name);
       ++P.launches;
+    } else if (op.kind == OP_FORK || op.kind == OP_JOIN) {
+      // stream structure only
     } else if (op.kind == OP_SOFTMAX) {
       resolve(P, op.s_view);
       RS_CHECK(op.s_view.C % 8 == 0 && op.s_view.C <= 8192 && op.s_view.ld % 8 == 0, "softmax row length");
@@ -835,22 +910,39 @@ inline bool op_skipped(const Op& op) {
     case OP_ATTN: return (skip >> 3) & 1;
     case OP_UPSAMPLE: return (skip >> 4) & 1;
     case OP_MLP: return (skip >> 5) & 1;
-    case OP_SOFTMAX: return false;
+    case OP_SOFTMAX: case OP_FORK: case OP_JOIN: return false;
   }
   return false;
 }
 
-int run_ops(rs_plan& P, const std::vector<Op>& ops, const float* film_base, long long film_sN, cudaStream_t st,
+int run_ops(rs_plan& P, const std::vector<Op>& ops, const float* film_base, long long film_sN, cudaStream_t st0,
             Prof* prof = nullptr) {
+  const bool multi = prof == nullptr && !P.side.empty();       // per-op timing runs everything on the caller's stream
   for (const Op& op : ops) {
     int rc = 0;
+    if (op.kind == OP_FORK || op.kind == OP_JOIN) {
+      if (multi) {
+        if (op.kind == OP_FORK) {
+          RS_CUDA_OK(cudaEventRecord(P.ev[0], st0));
+          for (cudaStream_t s : P.side) RS_CUDA_OK(cudaStreamWaitEvent(s, P.ev[0], 0));
+        } else {
+          for (size_t k = 0; k < P.side.size(); ++k) {
+            RS_CUDA_OK(cudaEventRecord(P.ev[k + 1], P.side[k]));
+            RS_CUDA_OK(cudaStreamWaitEvent(st0, P.ev[k + 1], 0));
+          }
+        }
+      }
+      if (prof) { cudaEventRecord(prof->get(), st0); prof->kind.push_back((int)OP_UPSAMPLE); cudaEventRecord(prof->get(), st0); }
+      continue;
+    }
+    cudaStream_t st = (multi && op.stream > 0 && op.stream <= (int)P.side.size()) ? P.side[op.stream - 1] : st0;
     if (op_skipped(op)) { if (prof) { cudaEventRecord(prof->get(), st); prof->kind.push_back((int)op.kind); cudaEventRecord(prof->get(), st); } continue; }
     if (prof) { cudaEventRecord(prof->get(), st); prof->kind.push_back((int)op.kind); }
     switch (op.kind) {
       case OP_CONV: rc = conv_launch(op.conv, st); break;
       case OP_GN: {
         GnDesc g = op.gn;
-        if (g.film_off >= 0) { g.film = film_base + g.film_off; g.film_sN = film_sN; }
+        if (g.film_off >= 0) { g.film = film_base + g.film_off + (long long)g.film_n0 * film_sN; g.film_sN = film_sN; }
         rc = gn_launch(g, st);
         break;
       }
@@ -1024,6 +1116,18 @@ int rs_plan_bind(rs_plan* p, void* workspace_dev) {
   if (p->fe_in.tens >= 0) { resolve(*p, p->fe_in); resolve(*p, p->lq_feat); }
   for (auto& kv : p->block_out) resolve(*p, kv.second);
   p->launches = 0;
+  if (p->branches > 1 && p->side.empty() && !p->sections.empty()) {
+    for (int k = 1; k < p->branches; ++k) {
+      cudaStream_t s = nullptr;
+      RS_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+      p->side.push_back(s);
+    }
+    for (int k = 0; k < p->branches; ++k) {
+      cudaEvent_t e = nullptr;
+      RS_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      p->ev.push_back(e);
+    }
+  }
   int rc = conv_init(); if (rc) return rc;
   rc = bind_ops(*p, p->fe_ops); if (rc) return rc;
   rc = bind_ops(*p, p->ops); if (rc) return rc;
@@ -1114,6 +1218,10 @@ int rs_plan_profile_ops(rs_plan* p, const float* x, const float* timesteps, cons
       snprintf(d, desc_stride, "mlp %dx%d E=%d Hd=%d grid=%d", op.mlp.in.H, op.mlp.in.W, op.mlp.E, op.mlp.Hd, op.mlp.grid);
     } else if (op.kind == OP_ATTN) {
       snprintf(d, desc_stride, "attn %dx%d shift=%d", op.a_in.H, op.a_in.W, op.a_shift);
+    } else if (op.kind == OP_FORK || op.kind == OP_JOIN) {
+      snprintf(d, desc_stride, "%s", op.kind == OP_FORK ? "fork" : "join");
+    } else if (op.kind == OP_SOFTMAX) {
+      snprintf(d, desc_stride, "softmax %d", op.s_view.C);
     } else {
       snprintf(d, desc_stride, "upsample %dx%d C=%d", op.u_in.H, op.u_in.W, op.u_in.C);
     }

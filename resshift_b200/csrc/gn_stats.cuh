@@ -205,44 +205,76 @@ __device__ __forceinline__ void pivot_stats2(Ld ld, int rows, float2& mean, floa
   m2 = make_float2(fmaxf(s2.x - s1.x * s1.x * inv, 0.f), fmaxf(s2.y - s1.y * s1.y * inv, 0.f));
 }
 
-// Column statistics of a staged output tile: [BN / bc blocks][128 rows][bc columns] fp16, 16-byte units XOR-swizzled
-// like the TMA box (Swizzle<B,4,3>: bc = 64 -> unit ^= row & 7, 32 -> (row >> 1) & 3, 16 -> (row >> 2) & 1).
-// Thread `tid` (< BN) takes column pair (tid % (BN/2)) of the 64-row half (tid / (BN/2)) and writes
-// wstat[half][col][2] = (mean, M2) for both columns.  Caller synchronises before reading wstat.
-__device__ __forceinline__ void staged_tile_column_stats(const uint8_t* stage, int BN, int bc, int tid, float* wstat) {
-  const int pairs = BN >> 1;
-  if (tid >= 2 * pairs) return;
-  const int half = tid / pairs, cp = tid - half * pairs;
-  const int col = 2 * cp;
-  const int blk = col / bc, cb = col - blk * bc;
-  const int u0 = cb >> 3, inner = (cb & 7) * 2;
-  const int pitch = 2 * bc;
-  const uint8_t* base = stage + (size_t)blk * (128 * pitch) + (size_t)(half * 64) * pitch + inner;
-  const int sh = (bc == 64) ? 0 : (bc == 32 ? 1 : 2);
-  const int msk = (bc == 64) ? 7 : (bc == 32 ? 3 : 1);
-  auto ld = [&](int r) {
-    const int rr = half * 64 + r;                                      // row inside the tile (swizzle uses the tile row)
-    const __half2 h = *reinterpret_cast<const __half2*>(base + (size_t)r * pitch + (((u0 ^ ((rr >> sh) & msk))) << 4));
-    return __half22float2(h);
-  };
-  // unrolled by 8 rows (the swizzle pattern has period 8): loads of a group are independent
-  const float2 p = ld(0);
-  float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
-  for (int r0 = 0; r0 < 64; r0 += 8) {
-    float2 v[8];
+// Statistics of one epilogue chunk while the accumulator tile drains: this warp's 32 rows x 16 columns, the values
+// exactly as stored (o0 / o1 = the two 16-byte units of fp16 the lane writes).  Transpose-reduce over the 32 lanes
+// (16 shuffles per moment, fixed tree), then (sum, sum of squares) -> (mean, M2) right here: over 32 fp16 values the
+// subtraction q - s^2/32 is benign (relative error ~1e-3 of M2 even for |mean| = 60 std), and every later combination
+// is Chan's formula on (mean, M2) pairs, so nothing down the line cancels.  dst = &wq[(quad * BN + c) * 2].
+__device__ __forceinline__ void warp_chunk_stats(const uint4& o0, const uint4& o1, int lane, float* dst) {
+  float sv[16], sq[16];
+  const __half2* q0 = reinterpret_cast<const __half2*>(&o0);
+  const __half2* q1 = reinterpret_cast<const __half2*>(&o1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = ld(r0 + j);
+  for (int j = 0; j < 4; ++j) {
+    const float2 x0 = __half22float2(q0[j]);
+    const float2 x1 = __half22float2(q1[j]);
+    sv[2 * j] = x0.x; sv[2 * j + 1] = x0.y; sv[8 + 2 * j] = x1.x; sv[8 + 2 * j + 1] = x1.y;
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float dx = v[j].x - p.x, dy = v[j].y - p.y;
-      s1.x += dx; s1.y += dy;
-      s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y);
+  for (int j = 0; j < 16; ++j) sq[j] = sv[j] * sv[j];
+#pragma unroll
+  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send_s = upper ? sv[j] : sv[j + half];
+      const float keep_s = upper ? sv[j + half] : sv[j];
+      sv[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+      const float send_q = upper ? sq[j] : sq[j + half];
+      const float keep_q = upper ? sq[j + half] : sq[j];
+      sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
     }
   }
-  const float inv = 1.0f / 64.0f;
-  float* dst = wstat + ((size_t)half * BN + col) * 2;
-  dst[0] = p.x + s1.x * inv; dst[1] = fmaxf(s2.x - s1.x * s1.x * inv, 0.f);
-  dst[2] = p.y + s1.y * inv; dst[3] = fmaxf(s2.y - s1.y * s1.y * inv, 0.f);
+  sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+  sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
+  if ((lane & 1) == 0) {
+    const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const float mean = sv[0] * (1.0f / 32.0f);
+    dst[cidx * 2] = mean;
+    dst[cidx * 2 + 1] = fmaxf(sq[0] - sv[0] * mean, 0.f);
+  }
+}
+
+// Final write of one tile's pairs from wq[4 quads][BN][2] (32 rows each, as produced above) into up to two sinks.
+// bn = images per tile (1: the four quads belong to image n0, ns = 128; 2: quads 0,1 -> n0 and 2,3 -> n0 + 1, ns = 64).
+__device__ __forceinline__ void write_quad_pairs(const float* wq, int BN, int ncols, int col0, int bn, int n0, int Nimg, int slot,
+                                                 int slots, const GnSink& s0, const GnSink& s1, int tid, int nthreads) {
+  for (int cc = tid; cc < ncols; cc += nthreads) {
+    float m[4], q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m[k] = wq[((size_t)k * BN + cc) * 2]; q[k] = wq[((size_t)k * BN + cc) * 2 + 1]; }
+    float ma, qa, mb, qb;
+    chan_merge_equal(32.f, m[0], q[0], m[1], q[1], ma, qa);
+    chan_merge_equal(32.f, m[2], q[2], m[3], q[3], mb, qb);
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const GnSink& s = d == 0 ? s0 : s1;
+      if (!s.part) continue;
+      const size_t ch = (size_t)s.coff + col0 + cc;
+      float* dst = s.part + (((size_t)n0 * slots + slot) * s.cstride + ch) * 2;
+      if (bn == 1) {
+        float mm, qq;
+        chan_merge_equal(64.f, ma, qa, mb, qb, mm, qq);
+        dst[0] = mm; dst[1] = qq;
+      } else {
+        dst[0] = ma; dst[1] = qa;
+        if (n0 + 1 < Nimg) {
+          float* dst1 = s.part + (((size_t)(n0 + 1) * slots + slot) * s.cstride + ch) * 2;
+          dst1[0] = mb; dst1[1] = qb;
+        }
+      }
+    }
+  }
 }
 
 // Final write of one tile's pairs from wstat[2 halves][BN][2] (as produced above, or by a plain [128][cw] column pass)
@@ -272,6 +304,44 @@ __device__ __forceinline__ void write_tile_pairs(const float* wstat, int BN, int
       }
     }
   }
+}
+
+// Consumer-side combine (GroupNorms whose producers do not finalise: the small UNet levels): (mean, M2) of ONE channel of
+// image n over all slots, single pass around the first slot's mean, 16 independent loads in flight.  Returns the
+// channel's mean and M2 over slots * ns values.
+__device__ __forceinline__ float2 gn_channel_from_pairs(const float* part_nc /* &part[n][0][c][0] */, int slots, int C, float ns) {
+  const float pivot = reinterpret_cast<const float2*>(part_nc)->x;
+  float s1 = 0.f, s2 = 0.f;
+  int sl = 0;
+  for (; sl + 16 <= slots; sl += 16) {
+    float2 e[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) e[u] = *reinterpret_cast<const float2*>(part_nc + (size_t)(sl + u) * C * 2);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { const float d = e[u].x - pivot; s1 += d; s2 += fmaf(ns * d, d, e[u].y); }
+  }
+  for (; sl + 4 <= slots; sl += 4) {
+    float2 e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) e[u] = *reinterpret_cast<const float2*>(part_nc + (size_t)(sl + u) * C * 2);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const float d = e[u].x - pivot; s1 += d; s2 += fmaf(ns * d, d, e[u].y); }
+  }
+  for (; sl < slots; ++sl) {
+    const float2 e = *reinterpret_cast<const float2*>(part_nc + (size_t)sl * C * 2);
+    const float d = e.x - pivot; s1 += d; s2 += fmaf(ns * d, d, e.y);
+  }
+  const float dm = s1 / (float)slots;
+  return make_float2(pivot + dm, fmaxf(s2 - ns * (float)slots * dm * dm, 0.f));
+}
+// ... and one group from its cpg channels' (mean, M2) (each over cnt values), sequential in channel order
+__device__ __forceinline__ float2 gn_group_from_channels(const float* ch_pairs /* [cpg][2] */, int cpg, float cnt, float eps) {
+  const float pivot = ch_pairs[0];
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = 0; j < cpg; ++j) { const float d = ch_pairs[2 * j] - pivot; s1 += d; s2 += fmaf(cnt * d, d, ch_pairs[2 * j + 1]); }
+  const float dm = s1 / (float)cpg;
+  const float m2 = fmaxf(s2 - cnt * (float)cpg * dm * dm, 0.f);
+  return make_float2(pivot + dm, rsqrtf(m2 / (cnt * (float)cpg) + eps));
 }
 
 #endif  // __CUDACC__

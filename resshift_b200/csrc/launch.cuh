@@ -39,7 +39,8 @@ inline PFN_encodeTiled get_encode_tiled() {
 struct View {
   __half* ptr = nullptr;   // resolved at bind time
   int tens = -1;           // owning workspace tensor
-  long long off = 0;       // element offset inside the tensor
+  long long off = 0;       // element offset inside the tensor (channel slice + batch slice)
+  int c0 = 0, n0 = 0;      // bookkeeping of the same slice: first channel / first image inside the owning tensor
   int N = 0, H = 0, W = 0, C = 0, ld = 0;
   long long sW() const { return ld; }
   long long sH() const { return (long long)W * ld; }
@@ -372,7 +373,7 @@ inline int conv_finalize(ConvDesc& d) {
       if (rc) return rc;
     }
     // the staging area (column blocks + per-warp GN partials) must fit in the operand ring
-    const size_t need = (size_t)msub * ((size_t)BN * kConvBM * 2 + (size_t)4 * BN * 2 * sizeof(float));
+    const size_t need = (size_t)msub * ((size_t)BN * kConvBM * 2 + (size_t)4 * BN * 2 * sizeof(float)) + 16;
     RS_CHECK(need <= (size_t)stages * stage_bytes, "epilogue staging does not fit in the pipeline shared memory");
   }
   // persistent variant (conv_persist.cuh) when the cost model chose it (every SM / pair gets at least two tiles), or
@@ -512,6 +513,7 @@ struct GnDesc {
   const float* gamma = nullptr; const float* beta = nullptr;
   const float* film = nullptr; long long film_sN = 0;   // resolved per launch for FiLM layers
   int film_off = -1;      // offset of this layer's [2C] slice inside an embedding row, or -1
+  int film_n0 = 0;        // first image of this (batch-sliced) op inside the plan's batch: row offset into per-image FiLM
   int silu = 0;
   float* part = nullptr;  // [N][slots][C][2] (mean, M2) pairs
   float* gstat = nullptr; // [N][32][2] (mean, rstd), finalised by the last producer CTA of each image
@@ -536,11 +538,11 @@ inline int gn_launch(const GnDesc& g, cudaStream_t st) {
   int chunks, rows;
   gn_chunks(HW, N, &chunks, &rows);
   int slots = g.slots;
-  RS_CHECK(g.gstat != nullptr, "GroupNorm needs the per-image group statistics buffer");
+  RS_CHECK(g.gstat != nullptr || g.part != nullptr, "GroupNorm needs a statistics buffer");
   if (!g.fused) {
     slots = chunks;
     const int lanes = 256 / (C / 8);
-    RS_CHECK(g.part != nullptr && g.counter != nullptr, "GroupNorm statistics buffers");
+    RS_CHECK(g.part != nullptr && (g.gstat == nullptr || g.counter != nullptr), "GroupNorm statistics buffers");
     GnStatsParams sp{};
     sp.x = g.in.ptr; sp.sN = g.in.sN(); sp.ld = g.in.ld; sp.C = C; sp.HW = HW; sp.N = N;
     sp.sink.part = g.part; sp.sink.gstat = g.gstat; sp.sink.counter = g.counter; sp.sink.cstride = C; sp.sink.coff = 0;
@@ -563,9 +565,8 @@ inline int gn_launch(const GnDesc& g, cudaStream_t st) {
     for (int cs = 2; actas * N * csplit < 222 && cs <= C / unit; ++cs)
       if (C % cs == 0 && (C / cs) % unit == 0) csplit = cs;
   }
-  GnApplyParams ap{g.in.ptr, g.in.sN(), g.in.ld, g.out.ptr, g.out.sN(), g.out.ld, C, HW, N, g.gstat,
+  GnApplyParams ap{g.in.ptr, g.in.sN(), g.in.ld, g.out.ptr, g.out.sN(), g.out.ld, C, HW, N, g.gstat, g.part, slots, g.eps,
                    g.gamma, g.beta, g.film, g.film_sN, g.silu, arows, C / csplit};
-  (void)slots;
   (void)launch_k(gn_apply_kernel, dim3(actas, N, csplit), dim3(256), (size_t)(4 * (C / csplit) + 64) * sizeof(float), st, ap);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
@@ -581,7 +582,8 @@ struct MlpDesc {
   GnSink sink[2] = {};
   long long* dbg = nullptr;
   // optional fused input GroupNorm (plain affine): `in` is then the un-normalised tensor
-  const float* gn_in_gstat = nullptr;
+  const float* gn_in_gstat = nullptr;      // finalised group statistics, or
+  const float* gn_in_part = nullptr; int gn_in_slots = 0;   // the producers' (mean, M2) pairs to combine in the kernel
   const float* gn_in_gamma = nullptr; const float* gn_in_beta = nullptr;
   MlpParams prm;
   int grid = 0; size_t smem = 0;
@@ -646,8 +648,10 @@ inline int mlp_finalize(MlpDesc& d) {
     if (rc) return rc;
   }
   p.dbg = d.dbg;
-  p.gn_in_gstat = d.gn_in_gstat; p.gn_in_gamma = d.gn_in_gamma; p.gn_in_beta = d.gn_in_beta;
-  RS_CHECK(!d.gn_in_gstat || (d.gn_in_gamma && d.gn_in_beta && d.Hd >= 4 * d.E && d.E % 32 == 0), "fused MLP: input GroupNorm arguments");
+  p.gn_in_gstat = d.gn_in_gstat; p.gn_in_part = d.gn_in_part; p.gn_in_slots = d.gn_in_slots;
+  p.gn_in_gamma = d.gn_in_gamma; p.gn_in_beta = d.gn_in_beta; p.gn_in_eps = 1e-5f;
+  RS_CHECK(!(d.gn_in_gstat || d.gn_in_part) || (d.gn_in_gamma && d.gn_in_beta && d.Hd >= 4 * d.E && d.E % 32 == 0),
+           "fused MLP: input GroupNorm arguments");
   p.gn_slots = p.tiles_w * p.tiles_h;
   {
     int k = 0;

@@ -52,7 +52,10 @@ struct MlpParams {
   // shared memory before the first GEMM — one gn_apply launch and one activation round trip less per Swin block.
   // Statistics arrive as the per-(image, group) pairs (mean, rstd) finalised by the producer (gn_stats.cuh), exactly
   // as gn_apply_kernel reads them: the operand equals what the separate pass would have stored, bit for bit.
-  const float* gn_in_gstat;          // [N][32][2] or nullptr
+  const float* gn_in_gstat;          // [N][32][2] finalised by the producer, or nullptr
+  const float* gn_in_part;           // [N][gn_in_slots][E][2] (mean, M2) pairs, combined here when gn_in_gstat == nullptr
+  int gn_in_slots;
+  float gn_in_eps;
   const float* gn_in_gamma;          // [E]
   const float* gn_in_beta;           // [E]
 };
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
     const bool el = elect_one();
     const uint32_t lead_x = mapa_u32(smem_u32(x_full), lead);
     if (el) {
-      if (p.gn_in_gstat) {
+      if (p.gn_in_gstat || p.gn_in_part) {
         // fused input GroupNorm: each CTA's GELU warps wait for their OWN tile, normalise it, then signal the leader
         mbar_arrive_expect_tx(x_full, (uint32_t)(kx * kTile));
         for (int kb = 0; kb < kx; ++kb) tma_load_4d(sX + (size_t)kb * kTile, &p.tmX, x_full, kb * kConvBK, w0, h0, n0);
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
         }
         if (dbg && el) dbg[c * 8 + 1] = clock64() - t_start;
       };
-      mbar_wait(p.gn_in_gstat ? x_ready : x_full, 0);
+      mbar_wait((p.gn_in_gstat || p.gn_in_part) ? x_ready : x_full, 0);
       tc_fence_after();
       gemm1(0);
       if (chunks > 1) gemm1(1);
@@ -247,19 +250,45 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
     const int r = quad * 32 + lane;
     const int etid = threadIdx.x;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    if (p.gn_in_gstat) {
+    if ((p.gn_in_gstat || p.gn_in_part)) {
       // ---- fused input GroupNorm: statistics -> per-(image, channel) affine -> X tile normalised in place ----
       // (same arithmetic and summation order as gn_apply_kernel, so the operand equals what the separate pass stored)
       const int E = p.E, cpg = E / 32;
       const int nimg = p.bn;                                       // images this tile touches (1 or 2)
+      float* s_mr = s_ab + 2 * E * 2;                              // [2][32][2] group (mean, rstd)
+      if (p.gn_in_gstat) {
+        if (etid < 32 * nimg) {
+          const int img = etid >> 5, g = etid & 31;
+          float2 mr = make_float2(0.f, 0.f);
+          if (n0 + img < p.Nimg) mr = ldcg_f2(p.gn_in_gstat + ((size_t)(n0 + img) * 32 + g) * 2);
+          s_mr[(img * 32 + g) * 2] = mr.x; s_mr[(img * 32 + g) * 2 + 1] = mr.y;
+        }
+      } else {
+        // combine the producers' pairs: same arithmetic and order as gn_apply_kernel (the operand must equal what the
+        // separate pass would have stored)
+        float* s_ch = s_b1;                                        // scratch [2][E][2] (bias1 is loaded afterwards)
+        const float ns = (float)(p.Hout * p.Wout) / (float)p.gn_in_slots;
+        for (int idx = etid; idx < nimg * E; idx += 32 * kMlpEpiWarps) {
+          const int img = idx / E, c = idx - img * E;
+          float2 mq = make_float2(0.f, 0.f);
+          if (n0 + img < p.Nimg)
+            mq = gn_channel_from_pairs(p.gn_in_part + (size_t)(n0 + img) * p.gn_in_slots * E * 2 + (size_t)c * 2, p.gn_in_slots, E, ns);
+          s_ch[(img * E + c) * 2] = mq.x; s_ch[(img * E + c) * 2 + 1] = mq.y;
+        }
+        named_bar_sync(1, 32 * kMlpEpiWarps);
+        if (etid < 32 * nimg) {
+          const int img = etid >> 5, g = etid & 31;
+          float chp[2 * 8];                                        // cpg <= 8 (E <= 256)
+          for (int j = 0; j < cpg; ++j) { chp[2 * j] = s_ch[(img * E + g * cpg + j) * 2]; chp[2 * j + 1] = s_ch[(img * E + g * cpg + j) * 2 + 1]; }
+          const float2 mr = gn_group_from_channels(chp, cpg, (float)(p.Hout * p.Wout), p.gn_in_eps);
+          s_mr[(img * 32 + g) * 2] = mr.x; s_mr[(img * 32 + g) * 2 + 1] = mr.y;
+        }
+      }
+      named_bar_sync(1, 32 * kMlpEpiWarps);
       for (int idx = etid; idx < nimg * E; idx += 32 * kMlpEpiWarps) {
         const int img = idx / E, c = idx - img * E, g = c / cpg;
-        float a = 0.f, b = 0.f;
-        if (n0 + img < p.Nimg) {
-          const float2 mr = ldcg_f2(p.gn_in_gstat + ((size_t)(n0 + img) * 32 + g) * 2);
-          a = mr.y * __ldg(p.gn_in_gamma + c);
-          b = __ldg(p.gn_in_beta + c) - mr.x * a;
-        }
+        const float a = s_mr[(img * 32 + g) * 2 + 1] * __ldg(p.gn_in_gamma + c);
+        const float b = __ldg(p.gn_in_beta + c) - s_mr[(img * 32 + g) * 2] * a;
         s_ab[(img * E + c) * 2] = a; s_ab[(img * E + c) * 2 + 1] = b;
       }
       named_bar_sync(1, 32 * kMlpEpiWarps);
@@ -286,6 +315,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
       fence_proxy_async_smem();                                     // the tensor core reads X through the async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(x_ready), lead));
+      named_bar_sync(1, 32 * kMlpEpiWarps);                         // the scratch aliasing the bias area is free again
     }
     for (int i = etid; i < p.Hd; i += 32 * kMlpEpiWarps) s_b1[i] = __ldg(p.bias1 + i);
     for (int i = etid; i < p.E; i += 32 * kMlpEpiWarps) s_b2[i] = __ldg(p.bias2 + i);
@@ -400,6 +430,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
         q1[i] = __floats2half2_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
       }
       *a0 = o0; *a1 = o1;
+      if (want_stats) warp_chunk_stats(o0, o1, lane, wsum + ((size_t)quad * p.E + c) * 2);
     }
     fence_proxy_async_smem();
     named_bar_sync(1, 32 * kMlpEpiWarps);
@@ -408,18 +439,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
       tma_store_commit();
     }
     if (want_stats) {
-      float* wstat = wsum;                                           // [2 halves][E][2]
-      int* s_flag = reinterpret_cast<int*>(wstat + 4 * p.E);
-      staged_tile_column_stats(sblk, p.E, 64, etid, wstat);
-      named_bar_sync(1, 32 * kMlpEpiWarps);
       const int slot = th * p.tiles_w + tw;
       if (n0 < p.Nimg)
-        write_tile_pairs(wstat, p.E, p.E, 0, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kMlpEpiWarps);
-      const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
-      const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
-      const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
-      const unsigned int ad[4] = {(unsigned)p.E, (unsigned)p.E, (unsigned)p.E, (unsigned)p.E};
-      gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kMlpEpiWarps, 1, s_flag);
+        write_quad_pairs(wsum, p.E, p.E, 0, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kMlpEpiWarps);
+      if (p.sink[0].gstat || p.sink[1].gstat) {
+        int* s_flag = reinterpret_cast<int*>(wsum + 8 * p.E);
+        const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
+        const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
+        const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
+        const unsigned int ad[4] = {(unsigned)p.E, (unsigned)p.E, (unsigned)p.E, (unsigned)p.E};
+        gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kMlpEpiWarps, 1, s_flag);
+      }
     }
     if (etid == 0) tma_store_wait_read();
     }
@@ -489,12 +519,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fused_sm100_kernel(const _
         const int slot = th * p.tiles_w + tw;
         if (n0 < p.Nimg)
           write_tile_pairs(s_col, cw, cw, cbase, p.bn, n0, p.Nimg, slot, p.gn_slots, p.sink[0], p.sink[1], etid, 32 * kMlpEpiWarps);
-        int* s_flag = reinterpret_cast<int*>(s_col + 4 * cw);
-        const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
-        const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
-        const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
-        const unsigned int ad[4] = {(unsigned)cw, (unsigned)cw, (unsigned)cw, (unsigned)cw};
-        gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kMlpEpiWarps, 1, s_flag);
+        if (p.sink[0].gstat || p.sink[1].gstat) {
+          int* s_flag = reinterpret_cast<int*>(s_col + 4 * cw);
+          const GnSink* const sk[4] = {&p.sink[0], &p.sink[0], p.sink[1].part ? &p.sink[1] : nullptr, p.sink[1].part ? &p.sink[1] : nullptr};
+          const int n1 = (p.bn == 2 && n0 + 1 < p.Nimg) ? n0 + 1 : -1;
+          const int im[4] = {n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1, n0 < p.Nimg ? n0 : -1, n0 < p.Nimg ? n1 : -1};
+          const unsigned int ad[4] = {(unsigned)cw, (unsigned)cw, (unsigned)cw, (unsigned)cw};
+          gn_arrive<4>(sk, im, ad, p.gn_slots, 128.0f / (float)p.bn, etid, 32 * kMlpEpiWarps, 1, s_flag);
+        }
       }
     }
   }

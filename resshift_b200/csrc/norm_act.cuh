@@ -30,7 +30,10 @@ struct GnApplyParams {
   const __half* x; long long x_sN; int x_ld;
   __half* y; long long y_sN; int y_ld;
   int C, HW, N;
-  const float* gstat;       // [N][32][2] = (group mean, group rstd)
+  const float* gstat;       // [N][32][2] = (group mean, group rstd) finalised by the producer, or nullptr: combine here
+  const float* part;        // [N][slots][C][2] (mean, M2) pairs (used when gstat == nullptr)
+  int slots;
+  float eps;
   const float* gamma;       // [C]
   const float* beta;        // [C]
   const float* film;        // optional [N or 1][2*C] : scale = film[0:C], shift = film[C:2C]
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ G
     float* dst = p.sink.part + (((size_t)n * p.slots + slot) * p.C + i) * 2;
     dst[0] = mean; dst[1] = m2;
   }
+  if (!p.sink.gstat) return;
   int* s_flag = reinterpret_cast<int*>(s_red + (size_t)lanes * p.C * 3);
   const GnSink* const sk[1] = {&p.sink};
   const int im[1] = {n};
@@ -132,10 +136,29 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p)
   // layer parameters do not depend on the producing kernel: fetch them while it drains
   for (int c = threadIdx.x; c < Cs; c += blockDim.x) { s_g[c] = __ldg(p.gamma + c0 + c); s_be[c] = __ldg(p.beta + c0 + c); }
   pdl_wait();
-  // the image's 32 (mean, rstd) pairs were finalised by the last producer CTA: one small read, then the affine
-  if (threadIdx.x < Cs / cpg) {
-    const float2 mr = ldcg_f2(p.gstat + ((size_t)n * 32 + c0 / cpg + threadIdx.x) * 2);
-    s_mean[threadIdx.x] = mr.x; s_rstd[threadIdx.x] = mr.y;
+  if (p.gstat) {
+    // the image's 32 (mean, rstd) pairs were finalised by the last producer CTA: one small read
+    if (threadIdx.x < Cs / cpg) {
+      const float2 mr = ldcg_f2(p.gstat + ((size_t)n * 32 + c0 / cpg + threadIdx.x) * 2);
+      s_mean[threadIdx.x] = mr.x; s_rstd[threadIdx.x] = mr.y;
+    }
+  } else {
+    // combine the producers' (mean, M2) pairs here (small tensors: a few slots): per channel over the slots, then per
+    // group over its channels — Chan's formula around pivots at both levels, fixed order
+    const float ns = (float)p.HW / (float)p.slots;
+    const float* part = p.part + (size_t)n * p.slots * p.C * 2 + (size_t)c0 * 2;
+    for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+      const float2 mq = gn_channel_from_pairs(part + (size_t)c * 2, p.slots, p.C, ns);
+      s_a[c] = mq.x; s_b[c] = mq.y;
+    }
+    __syncthreads();
+    if (threadIdx.x < Cs / cpg) {
+      const int g = threadIdx.x;
+      float chp[2 * 64];                                            // cpg <= 64 (C <= 2048)
+      for (int j = 0; j < cpg; ++j) { chp[2 * j] = s_a[g * cpg + j]; chp[2 * j + 1] = s_b[g * cpg + j]; }
+      const float2 mr = gn_group_from_channels(chp, cpg, (float)p.HW, p.eps);
+      s_mean[g] = mr.x; s_rstd[g] = mr.y;
+    }
   }
   __syncthreads();
   {

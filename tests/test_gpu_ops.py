@@ -199,7 +199,12 @@ def test_conv_statistics_finalised_by_last_cta(case, variant):
             y = torch.empty_like(out)
             _lib.check(G.L.rs_op_groupnorm_apply(out.data_ptr(), N, H, W, Co, Co, gamma.data_ptr(), beta.data_ptr(), None, 0, 0,
                                                  y.data_ptr(), Co, gstat.data_ptr(), G.stream()))
+            # the consumer-side combine of the same pairs (what the denoiser's small maps use) must agree with it
+            y2 = torch.empty_like(out)
+            _lib.check(G.L.rs_op_groupnorm_apply_pairs(out.data_ptr(), N, H, W, Co, Co, gamma.data_ptr(), beta.data_ptr(), None, 0, 0,
+                                                       y2.data_ptr(), Co, part.data_ptr(), max(1, H * W // 128), G.stream()))
             torch.cuda.synchronize()
+            assert (y2.float() - y.float()).abs().max().item() <= 2e-3 * (1 + y.float().abs().max().item())
             results.append((out, gstat.clone(), y))
     finally:
         for kk in env:
