@@ -217,6 +217,77 @@ def gpu_library_baseline(B: int, T: int, dev):
             "all_ms": ms}
 
 
+VQ_F4_GFLOP_PER_IMAGE = 1020.0      # VQ-GAN f4 encode + decode of one 256x256 image, 2*MACs
+
+
+def e2e_with_bookends(B: int, dev, steps: int, world: int = 1):
+    """images/s of the complete x4 super-resolution of B 64x64 uint8 images -> B 256x256 uint8 images on one GPU,
+    through ResShiftSampler (this package's native denoiser, VQ-GAN f4 and edge kernels), host buffers at both ends."""
+    import torch
+    from resshift_b200.config import preset
+    from resshift_b200.sampler import ResShiftSampler, make_configs
+    from resshift_b200.vq_arch import random_vq_state_dict, vq_preset
+    from resshift_b200.weights import random_state_dict
+    ucfg, dcfg = preset("realsr_journal", T_STEPS)
+    vcfg = vq_preset("f4")
+    ae = {"target": "ldm.models.autoencoder.VQModelTorch", "params": vcfg.to_kwargs(), "ckpt_path": random_vq_state_dict(vcfg, 0)}
+    s = ResShiftSampler(make_configs(ucfg, dcfg, autoencoder=ae, state_dict=random_state_dict(ucfg, 0)), sf=4, use_amp=True,
+                        chop_size=64, chop_stride=64, chop_bs=1, padding_offset=16, seed=12345)
+    g = torch.Generator().manual_seed(2024)
+    h_in = torch.randint(0, 256, (B, 64, 64, 3), dtype=torch.uint8, generator=g).pin_memory()
+    h_out = torch.empty(B, 256, 256, 3, dtype=torch.uint8).pin_memory()
+
+    def step():
+        d_in = h_in.to(dev, non_blocking=True)
+        out = s._process_u8(d_in, noise_repeat=False, bgr=True)
+        if world > 1:            # the final gather of north_star: uint8 [B/G, 256, 256, 3] shards over NCCL / NVLink
+            from resshift_b200 import parallel
+            allout = parallel.gather_shards(out, world * B)
+            out = allout[:B]
+        h_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    # stage breakdown with CUDA events (device-resident, one run each after the warm-up above)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    d_in = h_in.to(dev)
+    lq = torch.empty(B, 3, 64, 64, device=dev)
+    from resshift_b200 import _lib
+    _lib.check(_lib.lib.rs_op_ingest_u8(d_in.data_ptr(), B, 64, 64, 3, lq.data_ptr(), _lib.current_stream()))
+    diff, ae_m, model = s.base_diffusion, s.autoencoder, s.model
+    ev[0].record()
+    z_y = diff.encode_first_stage(lq, ae_m, up_sample=True)
+    ev[1].record()
+    z = diff.sample_latent(z_y, model, {"lq": lq})
+    ev[2].record()
+    img = ae_m.decode(z)
+    ev[3].record()
+    torch.cuda.synchronize()
+    enc_ms, loop_ms, dec_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+    peaks = _peaks()
+    vq_tflops = B * VQ_F4_GFLOP_PER_IMAGE * 1e9 / ((enc_ms + dec_ms) * 1e-3) / 1e12
+    return {"value": world * B / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "batch": B, "n_gpus": world,
+            "h2d_bytes_per_step": int(h_in.numel()), "d2h_bytes_per_step": int(h_out.numel()),
+            "stage_ms": {"bicubic_plus_vq_encode": enc_ms, "denoise_loop_15_steps_incl_noise_draw": loop_ms, "quantise_plus_vq_decode": dec_ms},
+            "vq_roofline": {"bound": "tensor", "achieved": vq_tflops, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
+                            "frac": vq_tflops / peaks["tensor_tflops"],
+                            "note": "VQ-GAN f4 encode + decode, 1.02 TFLOP per 256x256 image (SURVEY.md §8f), CUDA events around both"},
+            "what": "uint8 [B,64,64,3] pinned host -> H2D -> ingest -> bicubic x4 -> VQ-GAN f4 encode -> 15-step loop (CUDA graph) -> "
+                    "quantise + decode -> uint8 emit -> D2H [B,256,256,3]; random-init weights; wall clock per batch",
+            "nan": bool(torch.isnan(img).any().item())}
+
+
 def newest_ncu_summary():
     """(traffic bytes per GEMM launch, tensor-pipe % per kernel, file) from the newest profiles/*_ncu_full_summary.csv."""
     files = sorted((ROOT / "profiles").glob("*_ncu_full_summary.csv"), key=lambda p: p.stat().st_mtime)
@@ -394,6 +465,18 @@ def run_gpu(args):
     h2d = (h_zy.numel() + h_noise.numel() + h_lq.numel()) * 4
     d2h = h_out.numel() * 4
 
+    # ---- whole x4 path incl. the VQ-GAN bookends and the uint8 edges, host buffers in and out ------------------
+    # uint8 LQ images (pinned host) -> H2D -> ingest -> bicubic x4 -> VQ-GAN encode -> 15-step loop -> quantise + decode
+    # -> uint8 emit -> D2H: what ResShiftSampler.inference does per batch (reference sampler.py:176-223,286)
+    bookends = None
+    if not args.no_bookends:
+        try:
+            bookends = e2e_with_bookends(B, dev, max(2, min(args.steps, 3)), world)
+        except Exception as ex:
+            bookends = {"error": repr(ex)[:400]}
+        if rank == 0:
+            log("bookends done")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -511,6 +594,7 @@ def run_gpu(args):
         "gpu_launches": int(launches_per_loop * args.steps * 2),
         "launches_per_denoise_step": int(launches_per_forward - 6 + 1),
         "denoiser_tflops_per_gpu": step_tflops,
+        "e2e_with_bookends": bookends,
         "roofline": roofline, "cpu_baseline": cpu, "gpu_library_baseline": lib_base, "other_configs": other,
         "shard_parity": shard_parity, "clocks": clk,
     }
@@ -529,6 +613,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-bookends", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (A/B and ablation runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -300,6 +300,35 @@ def test_batch_independence_at_bench_size():
     assert mx <= FWD_MAX and mn <= FWD_MEAN
 
 
+def test_concurrent_batch_slices_are_bit_identical(monkeypatch):
+    """RS_LOWRES_STREAMS=2: the few-tile levels run as two batch slices on side streams (fork / join by events, captured
+    into the sampler's graph as parallel branches).  Per-image results do not depend on batch neighbours, but slices
+    get other tile configurations than the full batch, so the check is agreement to rounding — plus exact
+    reproducibility of the sliced plan itself, eager and graph-replayed, with per-image timesteps (FiLM rows)."""
+    from resshift_b200.models.script_util import create_gaussian_diffusion
+    outs = {}
+    for nb in ("1", "2"):
+        monkeypatch.setenv("RS_LOWRES_STREAMS", nb)
+        ucfg, dcfg, m = _model("tiny")
+        dcfg.sf = 1
+        diff = create_gaussian_diffusion(**dcfg.to_kwargs())
+        g = torch.Generator(device="cuda").manual_seed(5)
+        x = torch.randn(4, 3, 64, 64, device="cuda", generator=g)
+        lq = torch.rand(4, 3, 64, 64, device="cuda", generator=g) * 2 - 1
+        t = torch.tensor([3, 0, 2, 1], device="cuda")
+        noises = torch.randn(diff.num_timesteps + 1, 4, 3, 64, 64, device="cuda", generator=g)
+        f1 = m(x, t, lq=lq).clone()
+        assert torch.equal(f1, m(x, t, lq=lq))
+        a = diff.sample_latent(lq, m, {"lq": lq}, noises=noises, use_graph=True)
+        assert torch.equal(a, diff.sample_latent(lq, m, {"lq": lq}, noises=noises, use_graph=False))
+        outs[nb] = (f1, a)
+        del m
+    d = (outs["1"][0] - outs["2"][0]).abs().max().item()
+    e = (outs["1"][1] - outs["2"][1]).abs().max().item()
+    print(f"[streams] forward |d|max {d:.3e}, loop |d|max {e:.3e}")
+    assert d <= 1e-2 and e <= 1e-2
+
+
 def test_graph_replay_is_deterministic_and_matches_eager():
     from resshift_b200.models.script_util import create_gaussian_diffusion
     ucfg, dcfg, m = _model("tiny")
