@@ -201,6 +201,13 @@ int rs_op_groupnorm_apply_pairs(const void* x, int N, int H, int W, int C, int l
 int rs_op_expand_relpos(const float* table_225xh, float* dense_hx64x64, int heads, void* stream);
 int rs_op_window_attention(const void* qkv, int N, int H, int W, int heads, int shift, const float* bias_dense,
                            void* out, void* stream);
+/* fused attention half of a Swin block: y = x + proj(window_attention(qkv(norm1(x)))) (reference
+ * models/swin_transformer.py:246-275 with WindowAttention.forward :114-145); x NHWC fp16 [N,H,W,E] (in place when
+ * y == x), norm1 statistics as the producers' (mean, M2) pairs gn_part[N][gn_slots][E][2], weights packed fp16;
+ * part_out (optional): pairs of y per 8x8 window, [N][(H/8)*(W/8)][E][2] */
+int rs_op_swin_attn(const void* x, int N, int H, int W, int E, int heads, int shift, const float* gn_part, int gn_slots,
+                    const float* gamma, const float* beta, const void* wqkv_packed, const float* bqkv, const float* relbias_dense,
+                    const void* wproj_packed, const float* bproj, void* y, float* part_out, void* stream);
 /* fused Swin MLP (reference models/swin_transformer.py:17-33,279): out = residual + fc2(GELU(fc1(x))) */
 int rs_op_mlp(const void* x, int N, int H, int W, int E, int Hd, const void* w1_packed, const float* b1,
               const void* w2_packed, const float* b2, const void* residual, void* out, void* dbg_timeline_or_null,

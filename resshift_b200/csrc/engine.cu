@@ -257,7 +257,7 @@ int build_inventory(rs_engine& e) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-enum OpKind { OP_CONV, OP_GN, OP_ATTN, OP_UPSAMPLE, OP_MLP, OP_SOFTMAX, OP_FORK, OP_JOIN };
+enum OpKind { OP_CONV, OP_GN, OP_ATTN, OP_UPSAMPLE, OP_MLP, OP_SOFTMAX, OP_FORK, OP_JOIN, OP_SWIN_ATTN };
 
 struct Tensor {
   size_t bytes = 0;
@@ -282,6 +282,9 @@ struct Op {
   std::string in_param;
   // fused MLP
   MlpDesc mlp;
+  // fused attention half of a Swin block (norm1 + qkv + window attention + proj + residual)
+  SwinAttnDesc swin;
+  std::string blk_name;
   std::string w2_name, b2_name;
   std::string w_name, b_name, g_name;   // parameter names resolved at bind
   size_t stats_off = 0;                 // GroupNorm: offset of its (mean, M2) pair buffer inside the stats region
@@ -365,7 +368,7 @@ struct Builder {
   std::vector<Op>* cur;
   size_t stats_off = 0;
   int n_gn = 0;
-  struct Writer { int c0; int C; int n0; int N; int list; int op; };
+  struct Writer { int c0; int C; int n0; int N; int list; int op; int win_slots; };
   std::map<int, std::vector<Writer>> writers;      // tensor id -> latest writers by (channel range, image range)
   int cur_stream = 0;                              // ops are tagged with the stream of the batch slice being built
   int cur_batch0 = 0;                              // ... and with its first image inside the plan's batch (per-image FiLM rows)
@@ -375,10 +378,10 @@ struct Builder {
   static bool inside(const Writer& w, const View& v) {
     return w.c0 >= v.c0 && w.c0 + w.C <= v.c0 + v.C && w.n0 >= v.n0 && w.n0 + w.N <= v.n0 + v.N;
   }
-  void note_writer(const View& out, int C) {
+  void note_writer(const View& out, int C, int win_slots = 0) {
     auto& ws = writers[out.tens];
     ws.erase(std::remove_if(ws.begin(), ws.end(), [&](const Writer& w) { return overlaps(w, out, C); }), ws.end());
-    ws.push_back({out.c0, C, out.n0, out.N, list_id(), (int)cur->size() - 1});
+    ws.push_back({out.c0, C, out.n0, out.N, list_id(), (int)cur->size() - 1, win_slots});
   }
   // producers of every (channel, image) of `in` whose epilogues can deliver GroupNorm statistics (empty: not fusable)
   std::vector<Writer> covering_writers(const View& in) {
@@ -392,7 +395,7 @@ struct Builder {
         for (const Writer& w : it->second)
           if (inside(w, in)) { prod.push_back(w); covered += (long long)w.C * w.N; }
       bool ok = covered == (long long)in.C * in.N;
-      for (const Writer& w : prod) ok = ok && list(w.list)[w.op].stat_dst.size() < 2;
+      for (const Writer& w : prod) ok = ok && list(w.list)[w.op].stat_dst.size() < 2 && w.win_slots == prod[0].win_slots;
       if (!ok) prod.clear();
     }
     return prod;
@@ -402,6 +405,8 @@ struct Builder {
   // every MLP CTA combining the statistics itself (round 1) and with producer-finalised statistics (profiles/r2_s2:
   // 4.73 vs 4.69 ms per step) — and not faster either way, so it stays OFF (RS_MLP_NORM_FUSE=1 enables it)
   const bool fuse_mlp_norm = env_int("RS_MLP_NORM_FUSE", 0) != 0;
+  // norm1 + qkv + window attention + proj + residual as one kernel per Swin block (RS_SWIN_FUSE=0: four launches)
+  const bool fuse_swin_attn = env_int("RS_SWIN_FUSE", 1) != 0 && !env_is("RS_CONV_IMPL", "simt") && !env_is("RS_ATTN_IMPL", "simt");
   const bool fuse_stats = env_int("RS_GN_FUSE", 1) && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt");
   Builder(rs_plan& p) : P(p), E(*p.e), cur(&p.ops) {}
   int list_id() const { return cur == &P.fe_ops ? 0 : 1; }
@@ -441,8 +446,9 @@ struct Builder {
     op.g_name = name;
     // can the producers' epilogues deliver the statistics?  (every channel of every image of the view written by a
     // conv / MLP of this plan)
-    const int tile_slots = conv_tile_slots(in.H, in.W);
     std::vector<Writer> prod = covering_writers(in);
+    op.gn.win_slots = !prod.empty() && prod[0].win_slots;
+    const int tile_slots = op.gn.win_slots ? (in.H / 8) * (in.W / 8) : conv_tile_slots(in.H, in.W);
     int chunks, rows;
     gn_chunks(in.H * in.W, in.N, &chunks, &rows);
     op.gn.fused = !prod.empty();
@@ -478,7 +484,8 @@ struct Builder {
       prod = covering_writers(in);
       if (prod.empty() || Hd < 4 * E) return false;
       op.g_name = norm_name;
-      op.gn.in = in; op.gn.fused = true; op.gn.slots = conv_tile_slots(in.H, in.W);
+      op.gn.win_slots = prod[0].win_slots;
+      op.gn.in = in; op.gn.fused = true; op.gn.slots = op.gn.win_slots ? (in.H / 8) * (in.W / 8) : conv_tile_slots(in.H, in.W);
       op.stats_off = stats_off;
       op.gn_index = n_gn++;
       stats_off += align_up((size_t)in.N * op.gn.slots * in.C * 2 * sizeof(float), 256);
@@ -490,6 +497,29 @@ struct Builder {
     for (const Writer& w : prod)
       list(w.list)[w.op].stat_dst.push_back({list_id(), (int)cur->size() - 1, w.c0 - in.c0, w.n0 - in.n0});
     if (out.tens >= 0) note_writer(out, E);
+    return true;
+  }
+  // x <- x + proj(window_attention(qkv(norm1(x)))) in one kernel (swin_attn_fused.cuh); false when the statistics of x
+  // cannot come from its producers' epilogues
+  bool swin_attn(const View& x, const std::string& blk, int heads, int shift) {
+    std::vector<Writer> prod = covering_writers(x);
+    if (prod.empty()) return false;
+    Op op; op.kind = OP_SWIN_ATTN;
+    op.swin.x = x; op.swin.y = x; op.swin.heads = heads; op.swin.shift = shift;
+    op.blk_name = blk;
+    op.g_name = blk + ".norm1";
+    op.gn.win_slots = prod[0].win_slots;
+    op.gn.in = x; op.gn.fused = true; op.gn.slots = op.gn.win_slots ? (x.H / 8) * (x.W / 8) : conv_tile_slots(x.H, x.W);
+    op.stats_off = stats_off;
+    op.gn_index = n_gn++;
+    stats_off += align_up((size_t)x.N * op.gn.slots * x.C * 2 * sizeof(float), 256);
+    const int i = opi();
+    P.touch(x, i);
+    op.stream = cur_stream;
+    cur->push_back(op);
+    for (const Writer& w : prod)
+      list(w.list)[w.op].stat_dst.push_back({list_id(), (int)cur->size() - 1, w.c0 - x.c0, w.n0 - x.n0});
+    if (x.tens >= 0) note_writer(x, x.C, /*win_slots=*/1);
     return true;
   }
   void upsample(const View& in, const View& out) {
@@ -527,13 +557,16 @@ struct Builder {
     conv(x, p + ".patch_embed.proj", 1, 1, Ed, &e, nullptr, ACT_NONE);
     for (int i = 0; i < c.swin_depth; ++i) {
       const std::string b = p + ".blocks." + std::to_string(i);
-      View n1 = P.make_view(x.N, x.H, x.W, Ed);
-      gn(e, b + ".norm1", n1, 0, -1);
-      View qkv = P.make_view(x.N, x.H, x.W, 3 * Ed);
-      conv(n1, b + ".attn.qkv", 1, 1, 3 * Ed, &qkv, nullptr, ACT_NONE);
-      View a = P.make_view(x.N, x.H, x.W, Ed);
-      attn(qkv, a, b, (i % 2) ? shift_odd : 0);
-      conv(a, b + ".attn.proj", 1, 1, Ed, &e, &e, ACT_NONE);              // x = shortcut + attn
+      // x = x + proj(attn(qkv(norm1(x)))): one kernel (swin_attn_fused.cuh), or the four-launch sequence
+      if (!(fuse_swin_attn && swin_attn_supported(Ed, c.swin_heads, x.H, x.W) && swin_attn(e, b, c.swin_heads, (i % 2) ? shift_odd : 0))) {
+        View n1 = P.make_view(x.N, x.H, x.W, Ed);
+        gn(e, b + ".norm1", n1, 0, -1);
+        View qkv = P.make_view(x.N, x.H, x.W, 3 * Ed);
+        conv(n1, b + ".attn.qkv", 1, 1, 3 * Ed, &qkv, nullptr, ACT_NONE);
+        View a = P.make_view(x.N, x.H, x.W, Ed);
+        attn(qkv, a, b, (i % 2) ? shift_odd : 0);
+        conv(a, b + ".attn.proj", 1, 1, Ed, &e, &e, ACT_NONE);              // x = shortcut + attn
+      }
       const bool mlp_ok = fuse_mlp && mlp_supported(Ed, hidden, x.H, x.W, x.N);
       // x = x + fc2(gelu(fc1(norm2(x)))) in one kernel, norm2 applied to the X tile in shared memory
       if (mlp_ok && fuse_mlp_norm && mlp(e, b + ".mlp", Ed, hidden, e, e, b + ".norm2")) continue;
@@ -793,7 +826,7 @@ void resolve(rs_plan& P, View& v) {
 // the consumers combine the pairs themselves.  RS_GN_FINALIZE_SLOTS moves the threshold.
 bool gn_finalizes(const Op& g) {
   static const int thr = env_int("RS_GN_FINALIZE_SLOTS", 64);
-  return g.gn.slots > thr;
+  return g.gn.slots > thr && !g.gn.win_slots;      // (the fused Swin attention kernel delivers pairs only)
 }
 GnSink make_sink(rs_plan& P, const Op& g, int coff, int img_off = 0) {
   GnSink s{};
@@ -877,6 +910,30 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       op.a_bias = E.at<float>(op.w_name);
       RS_CHECK(op.a_bias != nullptr, "missing " + op.w_name);
       ++P.launches;
+    } else if (op.kind == OP_SWIN_ATTN) {
+      SwinAttnDesc& w = op.swin;
+      resolve(P, w.x); resolve(P, w.y);
+      const std::string& b = op.blk_name;
+      const Param* wq = E.find(b + ".attn.qkv.weight"); const Param* wp = E.find(b + ".attn.proj.weight");
+      RS_CHECK(wq && wp, "missing attention parameters of " + b);
+      w.wqkv = E.at<__half>(b + ".attn.qkv.weight"); w.wqkv_ld = wq->ipad; w.bqkv = E.at<float>(b + ".attn.qkv.bias");
+      w.wproj = E.at<__half>(b + ".attn.proj.weight"); w.wproj_ld = wp->ipad; w.bproj = E.at<float>(b + ".attn.proj.bias");
+      w.relbias = E.at<float>(b + ".attn.relative_position_bias_table");
+      w.gamma = E.at<float>(b + ".norm1.weight"); w.beta = E.at<float>(b + ".norm1.bias");
+      RS_CHECK(w.bqkv && w.bproj && w.relbias && w.gamma && w.beta, "missing attention parameters of " + b);
+      {
+        const GnSink sk = make_sink(P, op, 0);
+        w.gn_part = sk.part; w.gn_slots = op.gn.slots; w.gn_gstat = sk.gstat;
+      }
+      for (int i = 0; i < 2; ++i) {
+        w.sink[i] = GnSink{};
+        if (i < (int)op.stat_dst.size()) {
+          const Op::StatDst& sd = op.stat_dst[i];
+          w.sink[i] = make_sink(P, (sd.list == 0 ? P.fe_ops : P.ops)[sd.op], sd.coff, sd.img_off);
+        }
+      }
+      int rc = swin_attn_finalize(w); if (rc) return rc;
+      ++P.launches;
     } else if (op.kind == OP_FORK || op.kind == OP_JOIN) {
       // stream structure only
     } else if (op.kind == OP_SOFTMAX) {
@@ -914,6 +971,7 @@ inline bool op_skipped(const Op& op) {
     case OP_ATTN: return (skip >> 3) & 1;
     case OP_UPSAMPLE: return (skip >> 4) & 1;
     case OP_MLP: return (skip >> 5) & 1;
+    case OP_SWIN_ATTN: return (skip >> 3) & 1;
     case OP_SOFTMAX: case OP_FORK: case OP_JOIN: return false;
   }
   return false;
@@ -951,6 +1009,7 @@ int run_ops(rs_plan& P, const std::vector<Op>& ops, const float* film_base, long
         break;
       }
       case OP_MLP: rc = mlp_launch(op.mlp, st); break;
+      case OP_SWIN_ATTN: rc = swin_attn_launch(op.swin, st); break;
       case OP_ATTN:
         rc = attn_launch(op.a_in, op.a_out, op.a_bias, P.e->cfg.swin_heads, P.e->cfg.swin_embed_dim, op.a_shift, st);
         break;
@@ -1175,7 +1234,8 @@ int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const fl
   for (size_t i = 0; i < prof.kind.size(); ++i) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]);
-    ms_by_kind[prof.kind[i] == (int)OP_MLP ? 0 : prof.kind[i]] += ms;
+    const int kd = prof.kind[i];
+    ms_by_kind[kd == (int)OP_MLP ? 0 : (kd == (int)OP_SWIN_ATTN ? 2 : kd)] += ms;
   }
   double fl = 0.0; int nc = 0;
   for (const Op& op : p->ops) if (op.kind == OP_MLP) {
@@ -1222,6 +1282,8 @@ int rs_plan_profile_ops(rs_plan* p, const float* x, const float* timesteps, cons
       snprintf(d, desc_stride, "mlp %dx%d E=%d Hd=%d grid=%d", op.mlp.in.H, op.mlp.in.W, op.mlp.E, op.mlp.Hd, op.mlp.grid);
     } else if (op.kind == OP_ATTN) {
       snprintf(d, desc_stride, "attn %dx%d shift=%d", op.a_in.H, op.a_in.W, op.a_shift);
+    } else if (op.kind == OP_SWIN_ATTN) {
+      snprintf(d, desc_stride, "swin_attn %dx%d shift=%d grid=%d", op.swin.x.H, op.swin.x.W, op.swin.shift, op.swin.grid);
     } else if (op.kind == OP_FORK || op.kind == OP_JOIN) {
       snprintf(d, desc_stride, "%s", op.kind == OP_FORK ? "fork" : "join");
     } else if (op.kind == OP_SOFTMAX) {

@@ -15,6 +15,7 @@
 #include "mlp_fused.cuh"
 #include "norm_act.cuh"
 #include "window_attn.cuh"
+#include "swin_attn_fused.cuh"
 
 namespace rs {
 
@@ -207,6 +208,13 @@ inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn
           if (occ == 2 && ms * cand > 256) continue;                       // TMEM: 512 columns per SM
           const int budget = (occ == 2 ? 111 : 222) * 1024 - 2048;
           int st = std::min(std::min(8, std::max(2, num_kb)), budget / sbytes);
+          // the staged epilogue (output tile + statistics scratch) reuses the ring: it must be at least that large
+          // (short-K layers with wide channel tiles in pair mode: 2 stages x (16 KB + BN/2 x 128 B) < BN x 288 B)
+          {
+            const int st_need = (int)(((size_t)ms * ((size_t)cand * kConvBM * 2 + (size_t)4 * cand * 2 * sizeof(float)) + 16 + sbytes - 1) / sbytes);
+            if (st_need > budget / sbytes) continue;
+            st = std::max(st, st_need);
+          }
           if (f_stages) st = f_stages;
           if (st < 2 || (size_t)st * sbytes + 2304 > (size_t)(occ == 2 ? 113 : 227) * 1024) continue;
           const double smem_cycles = (sbytes + ms * (kConvBM * kConvBK * 2.0 + (cand / cg) * kConvBK * 2.0)) / 128.0;
@@ -245,7 +253,8 @@ inline TileConfig pick_tile_config(int m_tiles, int cout16, int num_kb, int f_bn
             const double part_bytes = 4.0 * m_tiles * 128.0 * cout16 * S;
             const double total = waves * round + (S == 1 ? 0.0 : mode == 1 ? 6000.0 : 19000.0 + 2.0 * part_bytes / 2048.0);
             if (total < best.est_cycles) {
-              best.est_cycles = total; best.BN = cand; best.msub = ms; best.stages = std::min(st, (int)std::max(2.0, kbs));
+              best.est_cycles = total; best.BN = cand; best.msub = ms;
+              best.stages = std::max(std::min(st, (int)std::max(2.0, kbs)), std::min(st, (int)(((size_t)ms * ((size_t)cand * kConvBM * 2 + (size_t)4 * cand * 2 * sizeof(float)) + 16 + sbytes - 1) / sbytes)));
               best.occ = occ; best.cg = cg; best.splitk = S; best.persist = 0; best.cluster_split = (S > 1 && mode == 1) ? 1 : 0;
               // what a wave really costs (timelines r1_s25): co-resident CTAs run in lockstep, so set-up, the first
               // operand round trip and the whole epilogue are exposed once per wave
@@ -471,6 +480,8 @@ inline int conv_init() {   // once per process, outside any stream capture
     RS_CUDA_OK(cudaFuncSetAttribute(conv_gemm_persist_sm100_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RS_CUDA_OK(cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     RS_CUDA_OK(cudaFuncSetAttribute(mlp_fused_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RS_CUDA_OK(cudaFuncSetAttribute(swin_attn_fused_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SwinSmem<192>::total));
+    RS_CUDA_OK(cudaFuncSetAttribute(swin_attn_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SwinSmem<64>::total));
     attr_set = true;
   }
   return 0;
@@ -521,6 +532,7 @@ struct GnDesc {
   float eps = 1e-5f;
   int slots = 0;
   bool fused = false;     // statistics already delivered by the producing kernels' epilogues
+  bool win_slots = false; // the producer is the fused Swin attention kernel: one slot per 8x8 window (64 values each)
 };
 
 inline void gn_chunks(int HW, int N, int* chunks, int* rows) {
@@ -669,6 +681,55 @@ inline int mlp_finalize(MlpDesc& d) {
 
 inline int mlp_launch(const MlpDesc& d, cudaStream_t st) {
   (void)launch_kc(mlp_fused_sm100_kernel, dim3(d.grid), dim3(kMlpThreads), d.smem, st, 2 * d.prm.hsplit, d.prm);
+  RS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- fused attention half of a Swin block (swin_attn_fused.cuh) ---------------------------------
+struct SwinAttnDesc {
+  View x, y;                               // input / output token tensors [N, H, W, E] (y may alias x)
+  int heads = 0, shift = 0;
+  const float* gn_part = nullptr; int gn_slots = 0; const float* gn_gstat = nullptr;
+  const float* gamma = nullptr; const float* beta = nullptr;
+  const __half* wqkv = nullptr; int wqkv_ld = 0; const float* bqkv = nullptr;
+  const float* relbias = nullptr;
+  const __half* wproj = nullptr; int wproj_ld = 0; const float* bproj = nullptr;
+  GnSink sink[2] = {};
+  SwinAttnParams prm;
+  int grid = 0;
+};
+inline bool swin_attn_supported(int E, int heads, int H, int W) {
+  return (E == 192 || E == 64) && heads * 32 == E && H % 8 == 0 && W % 8 == 0;
+}
+inline int swin_attn_finalize(SwinAttnDesc& d) {
+  SwinAttnParams& p = d.prm;
+  std::memset(&p, 0, sizeof(p));
+  const int E = d.x.C;
+  RS_CHECK(swin_attn_supported(E, d.heads, d.x.H, d.x.W), "fused Swin attention: E in {64, 192}, head_dim 32, H and W multiples of 8");
+  RS_CHECK(d.y.C == E && d.y.H == d.x.H && d.y.W == d.x.W && d.y.N == d.x.N, "fused Swin attention: output geometry");
+  RS_CHECK(d.x.ld % 8 == 0 && d.y.ld % 8 == 0 && d.wqkv_ld % 8 == 0 && d.wproj_ld % 8 == 0, "fused Swin attention: 16-byte rows");
+  RS_CHECK((d.gn_part && d.gn_slots > 0) || d.gn_gstat, "fused Swin attention: norm1 statistics");
+  p.x = d.x.ptr; p.x_ld = d.x.ld; p.y = d.y.ptr; p.y_ld = d.y.ld;
+  p.N = d.x.N; p.H = d.x.H; p.W = d.x.W; p.heads = d.heads; p.shift = d.shift; p.scale = 0.17677669529663687f;
+  p.gn_part = d.gn_part; p.gn_slots = d.gn_slots; p.gn_gstat = d.gn_gstat; p.gamma = d.gamma; p.beta = d.beta; p.eps = 1e-5f;
+  p.wqkv = d.wqkv; p.wqkv_ld = d.wqkv_ld; p.bqkv = d.bqkv; p.relbias = d.relbias;
+  p.wproj = d.wproj; p.wproj_ld = d.wproj_ld; p.bproj = d.bproj;
+  p.total_windows = d.x.N * (d.x.H / 8) * (d.x.W / 8);
+  {
+    int k = 0;
+    for (int i = 0; i < 2; ++i) {
+      if (!d.sink[i].part) continue;
+      p.sink[k] = d.sink[i]; p.sink[k].gstat = nullptr; p.sink[k].counter = nullptr;     // consumers combine the window pairs
+      ++k;
+    }
+  }
+  const int pairs = (p.total_windows + 1) / 2;
+  d.grid = std::min(pairs, 148);
+  return 0;
+}
+inline int swin_attn_launch(const SwinAttnDesc& d, cudaStream_t st) {
+  if (d.x.C == 192) (void)launch_k(swin_attn_fused_kernel<192>, dim3(d.grid), dim3(kSwinThreads), SwinSmem<192>::total, st, d.prm);
+  else (void)launch_k(swin_attn_fused_kernel<64>, dim3(d.grid), dim3(kSwinThreads), SwinSmem<64>::total, st, d.prm);
   RS_CUDA_OK(cudaGetLastError());
   return 0;
 }

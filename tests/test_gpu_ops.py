@@ -436,6 +436,82 @@ def test_window_attention(hw, shift, impl):
     assert st["nan"] == 0 and st["max_abs"] <= 4e-3 * ref.abs().max().item() + 2e-3, st
 
 
+@pytest.mark.parametrize("E", [192, 64])
+@pytest.mark.parametrize("case", [(2, 16, 32, 0), (2, 16, 32, 4), (3, 8, 8, 0), (1, 64, 64, 4), (5, 16, 16, 4)])
+def test_swin_attention_half_fused(case, E):
+    """norm1 + qkv + (shifted-)window attention + proj + residual as ONE kernel against plain torch on the same fp16
+    operands, with the intermediate roundings of the unfused path (fp16 n1 / qkv / attention output); also the
+    (mean, M2) pairs of the result per 8x8 window.  reference: models/swin_transformer.py:246-275,114-145."""
+    from resshift_b200.arch import relative_position_index, shifted_window_mask
+    N, H, W, shift = case
+    heads = E // 32
+    g = torch.Generator(device="cuda").manual_seed(E + H * 3 + shift + N)
+    x = (torch.randn(N, H, W, E, device="cuda", generator=g) * 1.5 + 0.3).half()
+    gamma = 1 + 0.2 * torch.randn(E, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(E, device="cuda", generator=g)
+    wqkv = torch.randn(3 * E, E, device="cuda", generator=g) / E ** 0.5
+    bqkv = torch.randn(3 * E, device="cuda", generator=g) * 0.1
+    wproj = torch.randn(E, E, device="cuda", generator=g) / E ** 0.5 * 0.5
+    bproj = torch.randn(E, device="cuda", generator=g) * 0.1
+    table = torch.randn(225, heads, device="cuda", generator=g) * 0.5
+    dense = torch.empty(heads * 64 * 64, dtype=torch.float32, device="cuda")
+    _lib.check(G.L.rs_op_expand_relpos(table.data_ptr(), dense.data_ptr(), heads, G.stream()))
+    # norm1 statistics as a producer would deliver them: (mean, M2) per (image, 128-pixel slot, channel); 8x8 maps have
+    # one 64-pixel slot per image
+    rows = 128 if H * W >= 128 else 64
+    slots = H * W // rows
+    xs = x.float().reshape(N, slots, rows, E)
+    mean_s = xs.mean(dim=2)
+    part = torch.stack([mean_s, ((xs - mean_s[:, :, None]) ** 2).sum(dim=2)], dim=-1).contiguous()
+    wq_p, _ = G.pack_weight(wqkv)
+    wp_p, _ = G.pack_weight(wproj)
+    nW = (H // 8) * (W // 8)
+    outs = []
+    for rep in range(2):
+        y = torch.full_like(x, float("nan"))
+        pout = torch.full((N, nW, E, 2), float("nan"), dtype=torch.float32, device="cuda")
+        _lib.check(G.L.rs_op_swin_attn(x.data_ptr(), N, H, W, E, heads, shift, part.data_ptr(), slots, gamma.data_ptr(), beta.data_ptr(),
+                                       wq_p.data_ptr(), bqkv.data_ptr(), dense.data_ptr(), wp_p.data_ptr(), bproj.data_ptr(),
+                                       y.data_ptr(), pout.data_ptr(), G.stream()))
+        torch.cuda.synchronize()
+        outs.append((y, pout))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    y, pout = outs[0]
+    # ---- reference (fp32 math on fp16-rounded operands, fp16 rounding where the unfused path stores) ----
+    xc = x.float().cpu()
+    xn = F.group_norm(xc.permute(0, 3, 1, 2), 32, gamma.cpu(), beta.cpu(), eps=1e-5).half().float()           # [N,E,H,W]
+    qkv = F.conv2d(xn, wqkv.half().float().cpu()[:, :, None, None], bqkv.cpu()).half().float()               # [N,3E,H,W]
+    if shift:
+        qkv = torch.roll(qkv, (-shift, -shift), (2, 3))
+    yw = qkv.reshape(N, 3 * E, H // 8, 8, W // 8, 8).permute(0, 2, 4, 3, 5, 1).reshape(-1, 64, 3, heads, 32)
+    qq, kk, vv = (yw[:, :, i].transpose(1, 2) for i in range(3))
+    attn = (qq * 32 ** -0.5) @ kk.transpose(-2, -1)
+    idx = relative_position_index(8).reshape(-1)
+    attn = attn + table.cpu()[idx].view(64, 64, heads).permute(2, 0, 1)[None]
+    if shift:
+        m = shifted_window_mask(H, W, 8, shift)
+        attn = (attn.view(-1, m.shape[0], heads, 64, 64) + m[None, :, None]).view(-1, heads, 64, 64)
+    o = (attn.softmax(-1) @ vv).transpose(1, 2).reshape(-1, 64, E)
+    o = o.view(N, H // 8, W // 8, 8, 8, E).permute(0, 5, 1, 3, 2, 4).reshape(N, E, H, W)
+    if shift:
+        o = torch.roll(o, (shift, shift), (2, 3))
+    o = o.half().float()
+    ref = (F.conv2d(o, wproj.half().float().cpu()[:, :, None, None], bproj.cpu()) + xc.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    st = G.err_stats(y.cpu(), ref)
+    print(f"[swin attn fused] E={E} {case}: {st}")
+    assert st["nan"] == 0 and st["max_abs"] <= 4e-3 * ref.abs().max().item() + 4e-3, st
+    # pairs of y per window (windows of the SHIFTED partition: statistics are over the same pixels the kernel owns)
+    yy = y.float().cpu().permute(0, 3, 1, 2)
+    if shift:
+        yy = torch.roll(yy, (-shift, -shift), (2, 3))
+    ywin = yy.reshape(N, E, H // 8, 8, W // 8, 8).permute(0, 2, 4, 1, 3, 5).reshape(N, nW, E, 64)
+    m_ref = ywin.mean(dim=3)
+    q_ref = ((ywin - m_ref[..., None]) ** 2).sum(dim=3)
+    assert not torch.isnan(pout).any()
+    assert (pout[..., 0].cpu() - m_ref).abs().max().item() <= 1e-4 * (1 + m_ref.abs().max().item())
+    assert ((pout[..., 1].cpu() - q_ref).abs() / (q_ref + 1e-3)).max().item() <= 2e-3
+
+
 def test_upsample_and_p_sample():
     g = torch.Generator(device="cuda").manual_seed(9)
     x = torch.randn(2, 8, 8, 64, device="cuda", generator=g).half()

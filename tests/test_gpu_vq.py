@@ -259,6 +259,8 @@ def test_tiled_pass_batched_tiles_match_tile_by_tile():
     u8 = ((im * 0.5 + 0.5) * 255).round().clamp(0, 255).byte().permute(0, 2, 3, 1).contiguous()
     out8 = s._process_u8(u8, noise_repeat=True, bgr=False)
     assert out8.shape == (1, 800, 592, 3) and out8.dtype == torch.uint8
-    lq_q = (u8.permute(0, 3, 1, 2).float() / 255.0 - 0.5) / 0.5
+    # (host-side numpy division like the reference's imread + transform: torch's CUDA division by a scalar multiplies by
+    # the reciprocal, and a last-bit difference in the input is enough to flip a code somewhere)
+    lq_q = torch.from_numpy((u8.cpu().numpy().astype(np.float32) / np.float32(255.0) - np.float32(0.5)) / np.float32(0.5)).permute(0, 3, 1, 2).contiguous().cuda()
     ref8 = (s._process(lq_q, noise_repeat=True).clamp(0, 1) * 255.0).round().byte().permute(0, 2, 3, 1)
     assert (out8.int() - ref8.int()).abs().max().item() <= 1
