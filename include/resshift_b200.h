@@ -139,6 +139,9 @@ int rs_vq_encode(rs_plan* p, const float* x, float* h_out, void* stream);
  * ldm/modules/vqvae/quantize.py:271-284; skipped when force_not_quantize) -> post_quant_conv -> Decoder -> [B, 3, H, W] fp32.
  * idx_out: optional [B, H/f, W/f] int32 code indices. */
 int rs_vq_decode(rs_plan* p, const float* h, float* out, int32_t* idx_out, int force_not_quantize, void* stream);
+/* diagnostics: per-launch times (ms) and descriptions of the plan's op list on the inputs of the last encode/decode
+ * call (counterpart of rs_plan_profile_ops for the first-stage plans) */
+int rs_vq_profile_ops(rs_plan* p, double* ms, char* desc, int desc_stride, int cap, int32_t* n_ops, void* stream);
 
 /* ---- image edges of the sampler (reference sampler.py:176-223,286; utils/util_image.py:216-273,889-979) --------- */
 /* F.interpolate(x, scale_factor=sf, mode='bicubic') on fp32 NCHW (models/gaussian_diffusion.py:503-504) */

@@ -406,7 +406,7 @@ struct Builder {
   // 4.73 vs 4.69 ms per step) — and not faster either way, so it stays OFF (RS_MLP_NORM_FUSE=1 enables it)
   const bool fuse_mlp_norm = env_int("RS_MLP_NORM_FUSE", 0) != 0;
   // norm1 + qkv + window attention + proj + residual as one kernel per Swin block (RS_SWIN_FUSE=0: four launches)
-  const bool fuse_swin_attn = env_int("RS_SWIN_FUSE", 1) != 0 && !env_is("RS_CONV_IMPL", "simt") && !env_is("RS_ATTN_IMPL", "simt");
+  const bool fuse_swin_attn = env_int("RS_SWIN_FUSE", 0) != 0 && !env_is("RS_CONV_IMPL", "simt") && !env_is("RS_ATTN_IMPL", "simt");
   const bool fuse_stats = env_int("RS_GN_FUSE", 1) && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt");
   Builder(rs_plan& p) : P(p), E(*p.e), cur(&p.ops) {}
   int list_id() const { return cur == &P.fe_ops ? 0 : 1; }
@@ -1252,18 +1252,9 @@ int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const fl
   return 0;
 }
 
-// Per-operator timing of one forward: fills ms[i] and a short description for each op of the main program.
-int rs_plan_profile_ops(rs_plan* p, const float* x, const float* timesteps, const float* lq, const float* mask,
-                        double* ms, char* desc, int desc_stride, int cap, int32_t* n_ops, void* stream) {
-  RS_CHECK(p && p->bound && ms && desc && n_ops, "bad argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  p->table_owner = nullptr;
-  int rc = run_embedding(*p, timesteps, p->B, st); if (rc) return rc;
-  rc = pack_lq_and_input(*p, x, lq, mask, nullptr, 0, st); if (rc) return rc;
-  Prof prof;
-  const float* film = reinterpret_cast<const float*>(p->ws + p->off_film);
-  rc = run_ops(*p, p->ops, film, p->e->film_rows, st, &prof); if (rc) return rc;
-  RS_CUDA_OK(cudaStreamSynchronize(st));
+// per-operator times + one-line descriptions of a profiled run_ops() pass
+static void collect_profile(const rs_plan& P, const Prof& prof, double* ms, char* desc, int desc_stride, int cap, int32_t* n_ops) {
+  const rs_plan* p = &P;
   const int n = std::min<int>((int)p->ops.size(), cap);
   *n_ops = n;
   for (int i = 0; i < n; ++i) {
@@ -1292,6 +1283,21 @@ int rs_plan_profile_ops(rs_plan* p, const float* x, const float* timesteps, cons
       snprintf(d, desc_stride, "upsample %dx%d C=%d", op.u_in.H, op.u_in.W, op.u_in.C);
     }
   }
+}
+
+// Per-operator timing of one forward: fills ms[i] and a short description for each op of the main program.
+int rs_plan_profile_ops(rs_plan* p, const float* x, const float* timesteps, const float* lq, const float* mask,
+                        double* ms, char* desc, int desc_stride, int cap, int32_t* n_ops, void* stream) {
+  RS_CHECK(p && p->bound && ms && desc && n_ops, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->table_owner = nullptr;
+  int rc = run_embedding(*p, timesteps, p->B, st); if (rc) return rc;
+  rc = pack_lq_and_input(*p, x, lq, mask, nullptr, 0, st); if (rc) return rc;
+  Prof prof;
+  const float* film = reinterpret_cast<const float*>(p->ws + p->off_film);
+  rc = run_ops(*p, p->ops, film, p->e->film_rows, st, &prof); if (rc) return rc;
+  RS_CUDA_OK(cudaStreamSynchronize(st));
+  collect_profile(*p, prof, ms, desc, desc_stride, cap, n_ops);
   return 0;
 }
 

@@ -382,8 +382,9 @@ inline int conv_finalize(ConvDesc& d) {
       if (rc) return rc;
     }
     // the staging area (column blocks + per-warp GN partials) must fit in the operand ring
+    // (the persistent kernel stages in buffers of its own, sized below)
     const size_t need = (size_t)msub * ((size_t)BN * kConvBM * 2 + (size_t)4 * BN * 2 * sizeof(float)) + 16;
-    RS_CHECK(need <= (size_t)stages * stage_bytes, "epilogue staging does not fit in the pipeline shared memory");
+    RS_CHECK(tc.persist || need <= (size_t)stages * stage_bytes, "epilogue staging does not fit in the pipeline shared memory");
   }
   // persistent variant (conv_persist.cuh) when the cost model chose it (every SM / pair gets at least two tiles), or
   // when RS_CONV_PERSIST = 1 forces it for any eligible layer
