@@ -200,6 +200,9 @@ int rs_op_groupnorm_apply(const void* x, int N, int H, int W, int C, int ld, con
 int rs_op_groupnorm_apply_pairs(const void* x, int N, int H, int W, int C, int ld, const float* gamma, const float* beta,
                                 const float* film, long long film_sN, int silu, void* y, int y_ld, const float* part,
                                 int slots, void* stream);
+/* group statistics gstat[N][32][2] = (mean, rstd) from (mean, M2) pairs part[N][slots][C][2] (rows_per_slot values each)
+ * as a kernel of its own — what the first-stage plans run in front of a GroupNorm whose producer has hundreds of tiles */
+int rs_op_groupnorm_finalize(const float* part, int N, int slots, int C, int rows_per_slot, float eps, float* gstat, void* stream);
 /* window attention core (reference models/swin_transformer.py:114-145,251-275); qkv [N,H,W,3*heads*32] */
 int rs_op_expand_relpos(const float* table_225xh, float* dense_hx64x64, int heads, void* stream);
 int rs_op_window_attention(const void* qkv, int N, int H, int W, int heads, int shift, const float* bias_dense,

@@ -85,6 +85,7 @@ _SIGNATURES = {
     "rs_op_groupnorm_scratch_floats": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "rs_op_groupnorm_apply": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_longlong, C.c_int,
                                         _P, C.c_int, _P, _P]),
+    "rs_op_groupnorm_finalize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
     "rs_op_groupnorm_apply_pairs": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_longlong,
                                               C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "rs_op_expand_relpos": (C.c_int, [_P, _P, C.c_int, _P]),

@@ -818,20 +818,28 @@ void resolve(rs_plan& P, View& v) {
   if (v.tens >= 0) v.ptr = reinterpret_cast<__half*>(P.ws + P.tensors[v.tens].off) + v.off;
 }
 
-// statistics destination of a producer: the consuming GroupNorm's pair buffer / group statistics / arrival counters
+// statistics destination of a producer: the consuming GroupNorm's pair buffer (+ group statistics / arrival counters)
 // (img_off: a producer that covers only images [img_off, ...) of the consumer — a batch slice on a side stream)
-// Producer-side finalisation (the last producer CTA of an image writes gstat) only pays for tensors with many tile slots
-// (the VQ-GAN's 128x128 / 256x256 maps: every consumer CTA would otherwise re-read slots x C pairs); on the denoiser's
-// small maps the arrival + reduction on the producer's tail costs more than it saves (profiles/r2_s1, r2_s2), so there
-// the consumers combine the pairs themselves.  RS_GN_FINALIZE_SLOTS moves the threshold.
+// Who reduces the (mean, M2) pairs to the image's 32 (mean, rstd)?
+//   * few tile slots (the denoiser's maps, <= 32 slots): every consumer CTA combines them itself — a finalisation step on
+//     the producer's tail costs more than it saves (profiles/r2_s1, r2_s2);
+//   * many slots (the VQ-GAN's 128x128 / 256x256 maps, RS_GN_FINALIZE_SLOTS moves the threshold): gn_finalize_kernel, a
+//     small launch in front of the consumer (default), or — RS_GN_PRODUCER_FINALIZE=1 — the last producer CTA of each
+//     image (arrival counters; measured +100 us per layer on one-tile CTAs and +800 us on the persistent kernel, whose
+//     CTAs all finish together so that ONE of them ends up reducing all 16 images: profiles/r2_s9_*).
 bool gn_finalizes(const Op& g) {
   static const int thr = env_int("RS_GN_FINALIZE_SLOTS", 64);
   return g.gn.slots > thr && !g.gn.win_slots;      // (the fused Swin attention kernel delivers pairs only)
 }
-GnSink make_sink(rs_plan& P, const Op& g, int coff, int img_off = 0) {
+bool gn_producer_finalizes(const Op& g) {
+  static const int on = env_int("RS_GN_PRODUCER_FINALIZE", 0);
+  // (a GroupNorm without a fusable producer runs gn_stats_kernel, whose few CTAs per image arrive themselves)
+  return gn_finalizes(g) && (on != 0 || !g.gn.fused);
+}
+GnSink make_sink(rs_plan& P, const Op& g, int coff, int img_off = 0, bool consumer = false) {
   GnSink s{};
   s.part = reinterpret_cast<float*>(P.ws + P.off_stats + g.stats_off) + (size_t)img_off * g.gn.slots * g.gn.in.C * 2;
-  if (gn_finalizes(g)) {
+  if (gn_producer_finalizes(g) || (consumer && gn_finalizes(g))) {
     s.gstat = reinterpret_cast<float*>(P.ws + P.off_gstat) + (size_t)g.gn_index * P.B * 64 + (size_t)img_off * 64;
     s.counter = reinterpret_cast<unsigned int*>(P.ws + P.off_counters) + (size_t)g.gn_index * P.B + img_off;
   }
@@ -878,10 +886,11 @@ int bind_ops(rs_plan& P, std::vector<Op>& ops) {
       op.gn.gamma = E.at<float>(op.g_name + ".weight"); op.gn.beta = E.at<float>(op.g_name + ".bias");
       RS_CHECK(op.gn.gamma && op.gn.beta, "missing GroupNorm parameters " + op.g_name);
       {
-        const GnSink sk = make_sink(P, op, 0);
+        const GnSink sk = make_sink(P, op, 0, 0, true);
         op.gn.part = sk.part; op.gn.gstat = sk.gstat; op.gn.counter = sk.counter;
+        op.gn.finalize_kernel = op.gn.fused && gn_finalizes(op) && !gn_producer_finalizes(op);
       }
-      P.launches += op.gn.fused ? 1 : 2;
+      P.launches += (op.gn.fused ? 1 : 2) + (op.gn.finalize_kernel ? 1 : 0);
     } else if (op.kind == OP_MLP) {
       MlpDesc& m = op.mlp;
       resolve(P, m.in); resolve(P, m.out); resolve(P, m.res);

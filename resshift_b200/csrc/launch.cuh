@@ -534,6 +534,7 @@ struct GnDesc {
   int slots = 0;
   bool fused = false;     // statistics already delivered by the producing kernels' epilogues
   bool win_slots = false; // the producer is the fused Swin attention kernel: one slot per 8x8 window (64 values each)
+  bool finalize_kernel = false;   // fused statistics with many slots: reduce part -> gstat with gn_finalize_kernel first
 };
 
 inline void gn_chunks(int HW, int N, int* chunks, int* rows) {
@@ -562,6 +563,12 @@ inline int gn_launch(const GnDesc& g, cudaStream_t st) {
     sp.sink.expected = (unsigned)(slots * C); sp.sink.eps = g.eps;
     sp.slots = slots; sp.rows_per_slot = rows;
     (void)launch_k(gn_stats_kernel, dim3(chunks, N), dim3(256), (size_t)lanes * C * 3 * sizeof(float) + 16, st, sp);
+    RS_CUDA_OK(cudaGetLastError());
+  }
+  if (g.fused && g.finalize_kernel) {
+    RS_CHECK(g.part != nullptr && g.gstat != nullptr && slots > 0 && HW % slots == 0, "GroupNorm finalisation buffers");
+    GnFinalizeParams fp{g.part, g.gstat, slots, C, (float)(HW / slots), g.eps};
+    (void)launch_k(gn_finalize_kernel, dim3(32, N), dim3(256), (size_t)0, st, fp);
     RS_CUDA_OK(cudaGetLastError());
   }
   // apply: ~4 CTAs per SM in total, all resident at once (each CTA re-derives the per-channel affine from the

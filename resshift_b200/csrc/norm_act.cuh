@@ -120,6 +120,61 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ G
   gn_arrive<1>(sk, im, ad, p.slots, (float)p.rows_per_slot, threadIdx.x, blockDim.x, 1, s_flag);
 }
 
+// Group statistics from the producers' pairs as a small kernel of its own: one CTA per (group, image), the K = slots * cpg
+// items of the group strided over 256 threads (4 loads in flight each), common pivot = item 0, fixed reduction order.
+// For tensors with hundreds of tile slots per image (the VQ-GAN's 128x128 / 256x256 maps) this beats both alternatives
+// measured in profiles/r2_s9_*: every consumer CTA re-reading slots x C pairs, and the last producer CTA reducing them on
+// the tail of a persistent conv kernel (one CTA ends up last for all 16 images: +800 us per layer).
+struct GnFinalizeParams {
+  const float* part;        // [N][slots][C][2]
+  float* gstat;             // [N][32][2] = (mean, rstd)
+  int slots, C;
+  float ns, eps;            // values per item (rows per slot)
+};
+
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const GnFinalizeParams p) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float s_w[8][2];
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int cpg = p.C >> 5;
+  const int K = p.slots * cpg;
+  const float* base = p.part + (size_t)n * p.slots * p.C * 2 + (size_t)g * cpg * 2;
+  const float pivot = ldcg_f2(base).x;
+  float s1 = 0.f, s2 = 0.f;
+  auto item = [&](int i) -> float2 {
+    const int sl = i / cpg, c = i - sl * cpg;
+    return ldcg_f2(base + ((size_t)sl * p.C + c) * 2);
+  };
+  int i = threadIdx.x;
+  for (; i + 3 * 256 < K; i += 4 * 256) {
+    float2 e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) e[u] = item(i + u * 256);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const float d = e[u].x - pivot; s1 += d; s2 += fmaf(p.ns * d, d, e[u].y); }
+  }
+  for (; i < K; i += 256) { const float2 e = item(i); const float d = e.x - pivot; s1 += d; s2 += fmaf(p.ns * d, d, e.y); }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_w[warp][0] = s1; s_w[warp][1] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += s_w[w][0]; b += s_w[w][1]; }
+    const float invK = 1.0f / (float)K;
+    const float dm = a * invK;
+    const float m2 = fmaxf(b - p.ns * (float)K * dm * dm, 0.f);
+    p.gstat[((size_t)n * 32 + g) * 2] = pivot + dm;
+    p.gstat[((size_t)n * 32 + g) * 2 + 1] = rsqrtf(m2 * invK / p.ns + p.eps);
+  }
+}
+
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p) {
   pdl_trigger();
   extern __shared__ float s_ab[];    // a[Cs], b[Cs], gamma[Cs], beta[Cs], mean[32], rstd[32]  (this CTA's channel slice)

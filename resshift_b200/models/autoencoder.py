@@ -81,6 +81,7 @@ class VQModelTorch(nn.Module):
 
     def pack_weights(self, force: bool = False):
         params = dict(self.named_parameters())
+        self._ensure_engine(next(iter(params.values())).device)      # (a no-op once the engine and its arena exist)
         versions = tuple((p._version, p.data_ptr()) for p in params.values())
         if not force and versions == self._packed_versions:
             return

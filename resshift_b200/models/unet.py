@@ -101,6 +101,7 @@ class UNetModelSwin(nn.Module):
     def pack_weights(self, force: bool = False):
         """(Re)pack parameters into the kernel-native fp16/fp32 arena when they changed."""
         params = dict(self.named_parameters())
+        self._ensure_engine(next(iter(params.values())).device)      # (a no-op once the engine and its arena exist)
         versions = tuple((p._version, p.data_ptr()) for p in params.values())
         if not force and versions == self._packed_versions:
             return

@@ -203,8 +203,14 @@ def test_conv_statistics_finalised_by_last_cta(case, variant):
             y2 = torch.empty_like(out)
             _lib.check(G.L.rs_op_groupnorm_apply_pairs(out.data_ptr(), N, H, W, Co, Co, gamma.data_ptr(), beta.data_ptr(), None, 0, 0,
                                                        y2.data_ptr(), Co, part.data_ptr(), max(1, H * W // 128), G.stream()))
+            # ... and so must the stand-alone finalisation kernel (what the first-stage plans run for many-slot tensors)
+            gstat3 = torch.full((N, 32, 2), float("nan"), dtype=torch.float32, device="cuda")
+            nsl = max(1, H * W // 128)
+            _lib.check(G.L.rs_op_groupnorm_finalize(part.data_ptr(), N, nsl, Co, H * W // nsl, 0.0, gstat3.data_ptr(), G.stream()))
             torch.cuda.synchronize()
             assert (y2.float() - y.float()).abs().max().item() <= 2e-3 * (1 + y.float().abs().max().item())
+            assert not torch.isnan(gstat3).any()
+            assert ((gstat3 - gstat).abs() <= 1e-4 * (1 + gstat.abs())).all(), (gstat3 - gstat).abs().max().item()
             results.append((out, gstat.clone(), y))
     finally:
         for kk in env:
