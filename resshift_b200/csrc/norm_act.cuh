@@ -191,8 +191,25 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p)
   // layer parameters do not depend on the producing kernel: fetch them while it drains
   for (int c = threadIdx.x; c < Cs; c += blockDim.x) { s_g[c] = __ldg(p.gamma + c0 + c); s_be[c] = __ldg(p.beta + c0 + c); }
   pdl_wait();
+  // the first rows of x do not depend on the statistics: put their loads in flight before the (latency-bound) statistics
+  // prologue below, so that its L2 round trips and barriers overlap the first data round trip
+  const int vecs = Cs >> 3;
+  const int lanes = blockDim.x / vecs;
+  const int vec = threadIdx.x % vecs, rl = threadIdx.x / vecs;
+  const bool active = rl < lanes;
+  const int c = vec * 8;
+  const int r0 = blockIdx.x * p.rows_per_cta;
+  const int r1 = min(r0 + p.rows_per_cta, p.HW);
+  const __half* xb = p.x + n * p.x_sN + c0 + c;
+  __half* yb = p.y + n * p.y_sN + c0 + c;
+  int r = r0 + rl;
+  constexpr int kPre = 4;
+  uint4 pre[kPre];
+#pragma unroll
+  for (int u = 0; u < kPre; ++u)
+    if (active && r + u * lanes < r1) pre[u] = *reinterpret_cast<const uint4*>(xb + (long long)(r + u * lanes) * p.x_ld);
   if (p.gstat) {
-    // the image's 32 (mean, rstd) pairs were finalised by the last producer CTA: one small read
+    // the image's 32 (mean, rstd) pairs were finalised by the producer side / gn_finalize_kernel: one small read
     if (threadIdx.x < Cs / cpg) {
       const float2 mr = ldcg_f2(p.gstat + ((size_t)n * 32 + c0 / cpg + threadIdx.x) * 2);
       s_mean[threadIdx.x] = mr.x; s_rstd[threadIdx.x] = mr.y;
@@ -202,9 +219,9 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p)
     // group over its channels — Chan's formula around pivots at both levels, fixed order
     const float ns = (float)p.HW / (float)p.slots;
     const float* part = p.part + (size_t)n * p.slots * p.C * 2 + (size_t)c0 * 2;
-    for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
-      const float2 mq = gn_channel_from_pairs(part + (size_t)c * 2, p.slots, p.C, ns);
-      s_a[c] = mq.x; s_b[c] = mq.y;
+    for (int cc = threadIdx.x; cc < Cs; cc += blockDim.x) {
+      const float2 mq = gn_channel_from_pairs(part + (size_t)cc * 2, p.slots, p.C, ns);
+      s_a[cc] = mq.x; s_b[cc] = mq.y;
     }
     __syncthreads();
     if (threadIdx.x < Cs / cpg) {
@@ -218,27 +235,19 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p)
   __syncthreads();
   {
     const float* f = p.film ? p.film + n * p.film_sN + c0 : nullptr;
-    for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
-      const int g = c / cpg;
-      float a = s_rstd[g] * s_g[c];
-      float b = s_be[c] - s_mean[g] * a;
-      if (f) { const float sc = 1.0f + f[c]; a *= sc; b = b * sc + f[p.C + c]; }
-      s_a[c] = a; s_b[c] = b;
+    for (int cc = threadIdx.x; cc < Cs; cc += blockDim.x) {
+      const int g = cc / cpg;
+      float a = s_rstd[g] * s_g[cc];
+      float b = s_be[cc] - s_mean[g] * a;
+      if (f) { const float sc = 1.0f + f[cc]; a *= sc; b = b * sc + f[p.C + cc]; }
+      s_a[cc] = a; s_b[cc] = b;
     }
   }
   __syncthreads();
-  const int vecs = Cs >> 3;
-  const int lanes = blockDim.x / vecs;
-  const int vec = threadIdx.x % vecs, rl = threadIdx.x / vecs;
-  if (rl >= lanes) return;
-  const int c = vec * 8;
+  if (!active) return;
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = s_a[c + j]; b[j] = s_b[c + j]; }
-  const int r0 = blockIdx.x * p.rows_per_cta;
-  const int r1 = min(r0 + p.rows_per_cta, p.HW);
-  const __half* xb = p.x + n * p.x_sN + c0 + c;
-  __half* yb = p.y + n * p.y_sN + c0 + c;
   auto one = [&](const uint4& raw) {
     const __half2* h = reinterpret_cast<const __half2*>(&raw);
     uint4 o;
@@ -253,7 +262,10 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const GnApplyParams p)
     }
     return o;
   };
-  int r = r0 + rl;
+#pragma unroll
+  for (int u = 0; u < kPre; ++u)
+    if (r + u * lanes < r1) *reinterpret_cast<uint4*>(yb + (long long)(r + u * lanes) * p.y_ld) = one(pre[u]);
+  r += kPre * lanes;
   for (; r + 7 * lanes < r1; r += 8 * lanes) {
     uint4 raw[8];
 #pragma unroll
