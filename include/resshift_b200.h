@@ -221,6 +221,9 @@ int rs_op_mlp(const void* x, int N, int H, int W, int E, int Hd, const void* w1_
 /* host-only: tile configuration the conv launcher picks: out[9] = BN, msub, stages, CTAs/SM, estimated cycles,
    CTAs per tile group (1 or 2), split-K factor, persistent kernel (0 / 1), cluster split-K (0 / 1) */
 int rs_debug_tile_config(int m_tiles, int cout, int num_kblocks, int32_t* out);
+/* profiling aid: later rs_op_swin_attn launches (tcgen05 kernel) write a clock64 timeline of CTA 0's first tile into
+ * dev_buf[64 x int64]; NULL switches it off */
+int rs_debug_swin_timeline(void* dev_buf_or_null);
 /* nearest x2 (reference models/unet.py:71-81) */
 int rs_op_upsample2x(const void* x, int N, int H, int W, int C, void* y, void* stream);
 

@@ -16,6 +16,7 @@
 #include "norm_act.cuh"
 #include "window_attn.cuh"
 #include "swin_attn_fused.cuh"
+#include "swin_attn_tc.cuh"
 
 namespace rs {
 
@@ -483,6 +484,8 @@ inline int conv_init() {   // once per process, outside any stream capture
     RS_CUDA_OK(cudaFuncSetAttribute(mlp_fused_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RS_CUDA_OK(cudaFuncSetAttribute(swin_attn_fused_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SwinSmem<192>::total));
     RS_CUDA_OK(cudaFuncSetAttribute(swin_attn_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SwinSmem<64>::total));
+    RS_CUDA_OK(cudaFuncSetAttribute(swin_attn_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SwinTcSmem<192>::total));
+    RS_CUDA_OK(cudaFuncSetAttribute(swin_attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SwinTcSmem<64>::total));
     attr_set = true;
   }
   return 0;
@@ -693,7 +696,8 @@ inline int mlp_launch(const MlpDesc& d, cudaStream_t st) {
   return 0;
 }
 
-// ---- fused attention half of a Swin block (swin_attn_fused.cuh) ---------------------------------
+// ---- fused attention half of a Swin block (swin_attn_fused.cuh, swin_attn_tc.cuh) -----------------
+static long long* g_swin_timeline = nullptr;   // rs_debug_swin_timeline
 struct SwinAttnDesc {
   View x, y;                               // input / output token tensors [N, H, W, E] (y may alias x)
   int heads = 0, shift = 0;
@@ -704,6 +708,9 @@ struct SwinAttnDesc {
   const __half* wproj = nullptr; int wproj_ld = 0; const float* bproj = nullptr;
   GnSink sink[2] = {};
   SwinAttnParams prm;
+  SwinTcParams tc;                         // tcgen05 version (swin_attn_tc.cuh): tensor maps of the two weight matrices
+  bool use_tc = false;
+  long long* dbg = nullptr;
   int grid = 0;
 };
 inline bool swin_attn_supported(int E, int heads, int H, int W) {
@@ -733,9 +740,23 @@ inline int swin_attn_finalize(SwinAttnDesc& d) {
   }
   const int pairs = (p.total_windows + 1) / 2;
   d.grid = std::min(pairs, 148);
+  // tcgen05 version unless RS_SWIN_IMPL=mma (the mma.sync kernel stays as the tested restatement of the same arithmetic)
+  d.use_tc = !env_is("RS_SWIN_IMPL", "mma") && d.wqkv_ld == E && d.wproj_ld == E;
+  if (d.use_tc) {
+    std::memset(&d.tc, 0, sizeof(d.tc));
+    d.tc.a = p; d.tc.dbg = d.dbg;
+    int rc = encode_weight_map(&d.tc.tmWqkv, d.wqkv, E, 3 * E, 64); if (rc) return rc;
+    rc = encode_weight_map(&d.tc.tmWproj, d.wproj, E, E, E); if (rc) return rc;
+  }
   return 0;
 }
 inline int swin_attn_launch(const SwinAttnDesc& d, cudaStream_t st) {
+  if (d.use_tc) {
+    if (d.x.C == 192) (void)launch_k(swin_attn_tc_kernel<192>, dim3(d.grid), dim3(kTcThreads), (size_t)SwinTcSmem<192>::total, st, d.tc);
+    else (void)launch_k(swin_attn_tc_kernel<64>, dim3(d.grid), dim3(kTcThreads), (size_t)SwinTcSmem<64>::total, st, d.tc);
+    RS_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (d.x.C == 192) (void)launch_k(swin_attn_fused_kernel<192>, dim3(d.grid), dim3(kSwinThreads), SwinSmem<192>::total, st, d.prm);
   else (void)launch_k(swin_attn_fused_kernel<64>, dim3(d.grid), dim3(kSwinThreads), SwinSmem<64>::total, st, d.prm);
   RS_CUDA_OK(cudaGetLastError());

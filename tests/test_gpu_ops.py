@@ -442,13 +442,15 @@ def test_window_attention(hw, shift, impl):
     assert st["nan"] == 0 and st["max_abs"] <= 4e-3 * ref.abs().max().item() + 2e-3, st
 
 
+@pytest.mark.parametrize("impl", ["tc", "mma"])
 @pytest.mark.parametrize("E", [192, 64])
 @pytest.mark.parametrize("case", [(2, 16, 32, 0), (2, 16, 32, 4), (3, 8, 8, 0), (1, 64, 64, 4), (5, 16, 16, 4)])
-def test_swin_attention_half_fused(case, E):
+def test_swin_attention_half_fused(case, E, impl, monkeypatch):
     """norm1 + qkv + (shifted-)window attention + proj + residual as ONE kernel against plain torch on the same fp16
     operands, with the intermediate roundings of the unfused path (fp16 n1 / qkv / attention output); also the
     (mean, M2) pairs of the result per 8x8 window.  reference: models/swin_transformer.py:246-275,114-145."""
     from resshift_b200.arch import relative_position_index, shifted_window_mask
+    monkeypatch.setenv("RS_SWIN_IMPL", impl)       # tc: tcgen05 kernel (swin_attn_tc.cuh); mma: mma.sync kernel (swin_attn_fused.cuh)
     N, H, W, shift = case
     heads = E // 32
     g = torch.Generator(device="cuda").manual_seed(E + H * 3 + shift + N)
@@ -504,7 +506,7 @@ def test_swin_attention_half_fused(case, E):
     o = o.half().float()
     ref = (F.conv2d(o, wproj.half().float().cpu()[:, :, None, None], bproj.cpu()) + xc.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
     st = G.err_stats(y.cpu(), ref)
-    print(f"[swin attn fused] E={E} {case}: {st}")
+    print(f"[swin attn fused {impl}] E={E} {case}: {st}")
     assert st["nan"] == 0 and st["max_abs"] <= 4e-3 * ref.abs().max().item() + 4e-3, st
     # pairs of y per window (windows of the SHIFTED partition: statistics are over the same pixels the kernel owns)
     yy = y.float().cpu().permute(0, 3, 1, 2)
