@@ -210,7 +210,10 @@ int rs_op_window_attention(const void* qkv, int N, int H, int W, int heads, int 
 /* fused attention half of a Swin block: y = x + proj(window_attention(qkv(norm1(x)))) (reference
  * models/swin_transformer.py:246-275 with WindowAttention.forward :114-145); x NHWC fp16 [N,H,W,E] (in place when
  * y == x), norm1 statistics as the producers' (mean, M2) pairs gn_part[N][gn_slots][E][2], weights packed fp16;
- * part_out (optional): pairs of y per 8x8 window, [N][(H/8)*(W/8)][E][2] */
+ * part_out (optional): pairs of y per 8x8 window, [N][(H/8)*(W/8)][E][2].  relbias_dense must be the output of
+ * rs_op_expand_relpos (relative_position_bias_table gathered by relative_position_index, :82-97,130-133): the tcgen05
+ * kernel keeps only its 225 distinct values per head (bias(i, j) depends on (yi - yj, xi - xj) alone).
+ * RS_SWIN_IMPL=mma selects the mma.sync kernel (same arithmetic, reads the dense table as given). */
 int rs_op_swin_attn(const void* x, int N, int H, int W, int E, int heads, int shift, const float* gn_part, int gn_slots,
                     const float* gamma, const float* beta, const void* wqkv_packed, const float* bqkv, const float* relbias_dense,
                     const void* wproj_packed, const float* bproj, void* y, float* part_out, void* stream);
@@ -222,7 +225,7 @@ int rs_op_mlp(const void* x, int N, int H, int W, int E, int Hd, const void* w1_
    CTAs per tile group (1 or 2), split-K factor, persistent kernel (0 / 1), cluster split-K (0 / 1) */
 int rs_debug_tile_config(int m_tiles, int cout, int num_kblocks, int32_t* out);
 /* profiling aid: later rs_op_swin_attn launches (tcgen05 kernel) write a clock64 timeline of CTA 0's first tile into
- * dev_buf[64 x int64]; NULL switches it off */
+ * dev_buf[128 x int64] (two tiles x 64 stamps); NULL switches it off */
 int rs_debug_swin_timeline(void* dev_buf_or_null);
 /* nearest x2 (reference models/unet.py:71-81) */
 int rs_op_upsample2x(const void* x, int N, int H, int W, int C, void* y, void* stream);

@@ -37,7 +37,7 @@ struct SwinTcParams {
   CUtensorMap tmWqkv;                   // {E, 3E} fp16, box {64, 64}
   CUtensorMap tmWproj;                  // {E, E} fp16, box {64, E}
   SwinAttnParams a;
-  long long* dbg;                       // optional: CTA 0 writes clock64 stamps of its first tile [64]
+  long long* dbg;                       // optional: CTA 0 writes clock64 stamps of its first two tiles [2][64]
 };
 
 constexpr int kTcWorkers = 256;
@@ -48,41 +48,55 @@ constexpr int kTcSlotBytes = 24576;     // one weight tile: 192 rows x 64 fp16
 template <int kE>
 struct SwinTcSmem {
   static constexpr int kKB = kE / 64;                       // 64-channel k-blocks = head groups
-  static constexpr int kSlots = kE == 192 ? 2 : 4;
-  static constexpr int off_xn = 0;                          // A operand of the QKV GEMMs; y staging in the epilogue
-  static constexpr int off_o = off_xn + kKB * 16384;        // A operand of the projection
-  static constexpr int off_q = off_o + kKB * 16384;         // [128 tokens][64 ch]  (2 heads)
+  static constexpr int kSlots = kE == 192 ? 3 : 4;          // three slots = one whole group of weight tiles in flight
+  static constexpr int off_xn = 0;                          // A operand of the QKV GEMMs; later O_1.. (k-blocks 1..) of the
+                                                            // projection's A operand; y staging in the epilogue
+  static constexpr int off_o = off_xn + kKB * 16384;        // O_0: k-block 0 of the projection's A operand (Xn is still live
+                                                            // when group 0 finishes; the later groups' O go into the dead Xn)
+  static constexpr int off_q = off_o + 16384;               // [128 tokens][64 ch]  (2 heads); Q / K / V^T later hold the residual
   static constexpr int off_k = off_q + 16384;               // [128 tokens][64 ch]
   static constexpr int off_vt = off_k + 16384;              // 2 token blocks x [64 ch][64 tokens]
   static constexpr int off_p = off_vt + 16384;              // 2 x [128 rows][64 keys]; norm1 scratch / statistics scratch
   static constexpr int off_ring = off_p + 32768;
   static constexpr int off_bars = off_ring + kSlots * kTcSlotBytes;
   static constexpr int off_pix = off_bars + 256;
-  static constexpr int total = off_pix + 512 + 1024;        // + slack for the 1024-byte alignment of the base
+  static constexpr int off_rpb = off_pix + 2 * 512;         // relative-position bias, compact: [heads][225] fp32
+  static constexpr int total = off_rpb + (kE / 32) * 225 * 4 + 1024;   // + slack for the 1024-byte alignment of the base
 };
 
 #ifdef __CUDACC__
 
-// 16 fp32 accumulator values (+ 16 biases) -> 16 fp16 in two 16-byte units
-__device__ __forceinline__ void tc_pack16(const uint32_t (&v)[16], const float* __restrict__ bias, uint4& o0, uint4& o1) {
+// 16 fp32 accumulator values + 16 biases -> 16 fp16 in two 16-byte units
+__device__ __forceinline__ void tc_pack16(const uint32_t (&v)[16], const float4 (&b)[4], uint4& o0, uint4& o1) {
   __half2* q0 = reinterpret_cast<__half2*>(&o0);
   __half2* q1 = reinterpret_cast<__half2*>(&o1);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + i);
-    const float f0 = __uint_as_float(v[4 * i]) + b.x, f1 = __uint_as_float(v[4 * i + 1]) + b.y;
-    const float f2 = __uint_as_float(v[4 * i + 2]) + b.z, f3 = __uint_as_float(v[4 * i + 3]) + b.w;
+    const float f0 = __uint_as_float(v[4 * i]) + b[i].x, f1 = __uint_as_float(v[4 * i + 1]) + b[i].y;
+    const float f2 = __uint_as_float(v[4 * i + 2]) + b[i].z, f3 = __uint_as_float(v[4 * i + 3]) + b[i].w;
     if (i < 2) { q0[2 * i] = __floats2half2_rn(f0, f1); q0[2 * i + 1] = __floats2half2_rn(f2, f3); }
     else { q1[2 * (i - 2)] = __floats2half2_rn(f0, f1); q1[2 * (i - 2) + 1] = __floats2half2_rn(f2, f3); }
   }
 }
-__device__ __forceinline__ void st_shared_u16(uint32_t addr, unsigned short v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+__device__ __forceinline__ float tc_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
+// warp-uniform NON-BLOCKING test of an mbarrier phase (every lane observes the completion); try_wait would suspend the
+// warp for its time-out on each unready barrier and make the issuer's polling loop react late
+__device__ __forceinline__ bool mbar_test_all(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return __all_sync(0xffffffffu, ok != 0 ? 1 : 0) != 0;
 }
 
 template <int kE>
@@ -96,7 +110,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
   const SwinAttnParams& p = prm.a;
 
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic on the __shared__ array itself: an integer round trip would lose the address space and turn every
+  //  plain access below into a generic LD / ST)
+  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   const uint32_t sb = smem_u32(smem);
   const uint32_t sXn = sb + L::off_xn, sO = sb + L::off_o, sQ = sb + L::off_q, sK = sb + L::off_k, sVT = sb + L::off_vt,
                  sP = sb + L::off_p, sRing = sb + L::off_ring;
@@ -112,7 +128,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
   uint64_t* o_ready = bars + 17;           // 8 worker warps
   uint64_t* y_full = bars + 18;            // commit
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  int* sPix = reinterpret_cast<int*>(smem + L::off_pix);    // [128] token -> pixel row, or -1
+  int* sPix2 = reinterpret_cast<int*>(smem + L::off_pix);   // [2][128] token -> pixel row, or -1 (this tile's / the next tile's)
+  float* sRpb = reinterpret_cast<float*>(smem + L::off_rpb);   // [heads][225]: bias(i, j) = sRpb[h][(yi - yj + 7) * 15 + (xi - xj + 7)]
   // scratch inside the P buffers (dead at the start and at the end of a tile)
   float* sAB = reinterpret_cast<float*>(smem + L::off_p);   // [2 windows][kE][2] affine of norm1
   float* sCh = sAB + 2 * kE * 2;                            // [2][kE][2] per-channel (mean, M2)
@@ -174,31 +191,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
                    idesc_proj = umma_idesc_f16(128, kE);
     int slot = 0; uint32_t ph = 0;
     uint32_t n_tile = 0, n_grp = 0;
-    auto issue_qkv = [&]() {
-      for (int kb = 0; kb < kKB; ++kb) {
-        mbar_wait(&w_full[slot], ph);
-        tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(sXn + (uint32_t)kb * 16384);
-        const uint64_t bdesc = umma_desc_sw128(sRing + (uint32_t)slot * kTcSlotBytes);
-        if (el) {
-          umma_f16(tmem_base, adesc, bdesc, idesc_qkv, kb != 0 ? 1u : 0u);
+    // one k-block of a QKV_g (N = 192) or projection (N = E) GEMM out of the weight ring
+    auto issue_kb = [&](uint32_t a_tile, int kb, uint32_t idesc, uint64_t* done_bar) {
+      const uint64_t adesc = umma_desc_sw128(a_tile);
+      const uint64_t bdesc = umma_desc_sw128(sRing + (uint32_t)slot * kTcSlotBytes);
+      if (el) {
+        umma_f16(tmem_base, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 1; k < 4; ++k) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc_qkv, 1u);
-          umma_commit(&w_empty[slot]);
-          if (kb == kKB - 1) umma_commit(acc_full);
-        }
-        if (++slot == kSlots) { slot = 0; ph ^= 1; }
+        for (int k = 1; k < 4; ++k) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+        umma_commit(&w_empty[slot]);
+        if (kb == kKB - 1) umma_commit(done_bar);
       }
+      __syncwarp();
+      if (++slot == kSlots) { slot = 0; ph ^= 1; }
+    };
+    auto issue_pv = [&](int j) {
+      if (el) {
+        const uint64_t pd = umma_desc_sw128(sP + (uint32_t)j * 16384);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const uint64_t vd = umma_desc_sw128(sVT + (uint32_t)w * 8192 + (uint32_t)j * 4096);
+          const uint32_t d = tmem_base + (j ? kTmS1 : kTmS0) + 32 * w;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(d, pd + 2 * k, vd + 2 * k, idesc_pv, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[j]);
+      }
+      __syncwarp();
     };
     for (int pair = pair_begin; pair < pair_end; ++pair) {
       mbar_wait(xn_full, n_tile & 1);
       tc_fence_after();
-      if (dbg && el && n_tile == 0) dbg[32] = clock64() - t_start;
-      issue_qkv();
+      if (dbg && el && n_tile < 2) dbg[64 * n_tile + 32] = clock64() - t_start;
+      for (int kb = 0; kb < kKB; ++kb) {
+        mbar_wait(&w_full[slot], ph);
+        tc_fence_after();
+        issue_kb(sXn + (uint32_t)kb * 16384, kb, idesc_qkv, acc_full);
+      }
       for (int g = 0; g < kG; ++g) {
         mbar_wait(qkv_drained, n_grp & 1);
         tc_fence_after();
-        if (dbg && el && n_tile == 0) dbg[33 + g * 4] = clock64() - t_start;
+        if (dbg && el && n_tile < 2) dbg[64 * n_tile + 33 + g * 4] = clock64() - t_start;
         // S_j = Q_h K_h^T for the two heads of the group: per window (key block) one N = 64 accumulator
         if (el) {
 #pragma unroll
@@ -215,45 +248,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
           }
         }
         __syncwarp();
-        if (g + 1 < kG) issue_qkv();                         // the next group's GEMM runs under this group's softmax
+        // the next group's QKV GEMM runs under this group's softmax; PV_j goes out as soon as P_j is written — whichever
+        // of the two is ready first (a k-block waiting for its weight tile must not hold back a finished head)
+        int kb_next = (g + 1 < kG) ? 0 : kKB;
+        // last group: the projection's k-blocks 0 .. kKB-2 (O of the earlier groups, complete and fenced before this group's
+        // drain arrived) go out under the softmax as well; only the last one waits for O of this group
+        int pj_next = 0;
+        const int pj_early = (g + 1 < kG) ? 0 : kKB - 1;
+        uint32_t pv_done = 0;
+        uint32_t spins = 0;
+        const uint64_t t0 = global_timer_ns();
+        while (kb_next < kKB || pj_next < pj_early || pv_done != 3u) {
+          bool progressed = false;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          mbar_wait(&p_full[j], n_grp & 1);
-          tc_fence_after();
-          if (dbg && el && n_tile == 0) dbg[34 + g * 4 + j] = clock64() - t_start;
-          if (el) {
-            const uint64_t pd = umma_desc_sw128(sP + (uint32_t)j * 16384);
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-              const uint64_t vd = umma_desc_sw128(sVT + (uint32_t)w * 8192 + (uint32_t)j * 4096);
-              const uint32_t d = tmem_base + (j ? kTmS1 : kTmS0) + 32 * w;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d, pd + 2 * k, vd + 2 * k, idesc_pv, k != 0 ? 1u : 0u);
+          for (int j = 0; j < 2; ++j) {
+            if (!(pv_done & (1u << j)) && mbar_test_all(&p_full[j], n_grp & 1)) {
+              tc_fence_after();
+              if (dbg && el && n_tile < 2) dbg[64 * n_tile + 34 + g * 4 + j] = clock64() - t_start;
+              issue_pv(j);
+              pv_done |= 1u << j;
+              progressed = true;
             }
-            umma_commit(&o_full[j]);
           }
-          __syncwarp();
+          if (kb_next < kKB && mbar_test_all(&w_full[slot], ph)) {
+            tc_fence_after();
+            issue_kb(sXn + (uint32_t)kb_next * 16384, kb_next, idesc_qkv, acc_full);
+            ++kb_next;
+            progressed = true;
+          }
+          if (pj_next < pj_early && mbar_test_all(&w_full[slot], ph)) {
+            tc_fence_after();
+            issue_kb(pj_next == 0 ? sO : sXn + (uint32_t)pj_next * 16384, pj_next, idesc_proj, y_full);
+            ++pj_next;
+            progressed = true;
+          }
+          if (!progressed) {
+            // back off: a tight test_wait loop would take issue slots from the two worker warps of this scheduler
+            __nanosleep(40);
+            if ((++spins & 0xFFu) == 0 && global_timer_ns() - t0 > 2000000000ull) {
+              if (lane == 0) printf("rs: swin tc issuer timeout (block %d group %d)\n", blockIdx.x, g);
+              __trap();
+            }
+          }
         }
         ++n_grp;
       }
       mbar_wait(o_ready, n_tile & 1);
       tc_fence_after();
-      if (dbg && el && n_tile == 0) dbg[46] = clock64() - t_start;
-      for (int kb = 0; kb < kKB; ++kb) {
+      if (dbg && el && n_tile < 2) dbg[64 * n_tile + 46] = clock64() - t_start;
+      for (int kb = kKB - 1; kb < kKB; ++kb) {               // (k-blocks 0 .. kKB-2 went out during the last group)
         mbar_wait(&w_full[slot], ph);
         tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(sO + (uint32_t)kb * 16384);
-        const uint64_t bdesc = umma_desc_sw128(sRing + (uint32_t)slot * kTcSlotBytes);
-        if (el) {
-          umma_f16(tmem_base, adesc, bdesc, idesc_proj, kb != 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 1; k < 4; ++k) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc_proj, 1u);
-          umma_commit(&w_empty[slot]);
-          if (kb == kKB - 1) umma_commit(y_full);
-        }
-        if (++slot == kSlots) { slot = 0; ph ^= 1; }
+        issue_kb(kb == 0 ? sO : sXn + (uint32_t)kb * 16384, kb, idesc_proj, y_full);
       }
-      if (dbg && el && n_tile == 0) dbg[47] = clock64() - t_start;
+      if (dbg && el && n_tile < 2) dbg[64 * n_tile + 47] = clock64() - t_start;
       ++n_tile;
     }
   } else {
@@ -263,14 +311,69 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
     const int wi = r >> 6, ti = r & 63;                      // window of the pair, token inside the window
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t tm_row = tmem_base + lane_base;
-    const uint32_t rsw = (uint32_t)(r & 7);
+    const int rsw = r & 7;
+    uint8_t* const pXn = smem + L::off_xn;                   // (plain C++ stores: the compiler may schedule them freely;
+    uint8_t* const pO = smem + L::off_o;                     //  the phase-closing fences / arrivals are the ordering points)
+    uint8_t* const pQ = smem + L::off_q;
+    uint8_t* const pK = smem + L::off_k;
+    uint8_t* const pVT = smem + L::off_vt;
+    uint8_t* const pP = smem + L::off_p;
     uint32_t n_tile = 0, n_grp = 0;
     int cur_img[2] = {-1, -1};
+    // gather / store geometry: a thread keeps ONE 16-byte unit (8 channels) and walks rows
+    constexpr int kRowLanes = kTcWorkers / kUnits;           // 10 (E = 192: 240 threads active) / 32 (E = 64)
+    constexpr int kIt = (64 + kRowLanes - 1) / kRowLanes;    // row iterations per window: 7 / 2
+    const int gu = tid % kUnits, gr0 = tid / kUnits;
+    const bool gact = gr0 < kRowLanes;
+    const float kLog2e = 1.4426950408889634f;
+    // pixel table of a window pair + gather of its 128 token rows (raw x) straight into their operand positions
+    // (cp.async); the thread that copied a unit later normalises it: no barrier between copy and use
+    auto issue_gather = [&](int pr, int* pix_tab) {
+      if (tid < 128) {
+        const int k = tid >> 6, tok = tid & 63;
+        const int w2 = 2 * pr + k;
+        int pix = -1;
+        if (w2 < p.total_windows) {
+          const int n = w2 / nW, rem = w2 % nW, wy = rem / nWx, wx = rem % nWx;
+          const int yy = (wy * 8 + (tok >> 3) + p.shift) % p.H, xx = (wx * 8 + (tok & 7) + p.shift) % p.W;
+          pix = (n * p.H + yy) * p.W + xx;
+        }
+        pix_tab[tid] = pix;
+      }
+      named_bar_sync(1, kTcWorkers);
+      if (gact) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int it = 0; it < kIt; ++it) {
+            const int lr = gr0 + it * kRowLanes;
+            if (lr < 64) {
+              const int row = k * 64 + lr;
+              const int pix = pix_tab[row];
+              uint8_t* dst = pXn + (gu >> 3) * 16384 + row * 128 + (((gu & 7) ^ (row & 7)) << 4);
+              if (pix >= 0) cp_async_16(dst, p.x + (long long)pix * p.x_ld + gu * 8);
+              else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+            }
+          }
+      }
+      cp_async_commit();
+    };
+    // The dense [heads][64][64] bias is relative_position_bias_table gathered by relative_position_index (reference
+    // models/swin_transformer.py:82-97,130-133): it depends on (yi - yj, xi - xj) only.  Keep the 225 distinct values per
+    // head in shared memory (5.4 KB) — fetching each warp's 8 KB block of the dense table from L2 for every head of every
+    // tile made all SMs hit the same few lines at the same time and cost ~3000 cycles per group (profiles/r2_s19).
+    for (int t = tid; t < (kE / 32) * 225; t += kTcWorkers) {
+      const int h = t / 225, d = t - h * 225;
+      const int dy = d / 15 - 7, dx = d % 15 - 7;
+      const int i = max(dy, 0) * 8 + max(dx, 0), j = max(-dy, 0) * 8 + max(-dx, 0);
+      sRpb[t] = __ldg(p.relbias + ((size_t)h * 64 + i) * 64 + j);
+    }
     pdl_wait();
 
     for (int pair = pair_begin; pair < pair_end; ++pair) {
-      const bool stamp = dbg && tid == 0 && n_tile == 0;
-      if (stamp) dbg[0] = clock64() - t_start;
+      const bool stamp = dbg && tid == 0 && n_tile < 2;
+      long long* const dbgw = dbg + 64 * (n_tile & 1);
+      if (stamp) dbgw[0] = clock64() - t_start;
       // ---- geometry of the two windows ----
       int n_img[2], wy_[2];
 #pragma unroll
@@ -279,163 +382,182 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
         n_img[k] = w2 / nW;
         wy_[k] = (w2 % nW) / nWx;
       }
-      if (tid < 128) {
-        const int k = tid >> 6, tok = tid & 63;
-        const int w2 = 2 * pair + k;
-        int pix = -1;
-        if (w2 < p.total_windows) {
-          const int n = w2 / nW, rem = w2 % nW, wy = rem / nWx, wx = rem % nWx;
-          const int yy = (wy * 8 + (tok >> 3) + p.shift) % p.H, xx = (wx * 8 + (tok & 7) + p.shift) % p.W;
-          pix = (n * p.H + yy) * p.W + xx;
-        }
-        sPix[tid] = pix;
-      }
-      named_bar_sync(1, kTcWorkers);
-      // ---- gather the 128 token rows (raw x) into registers: the loads fly while the affine is derived ----
-      constexpr int kPer = 128 * kUnits / kTcWorkers;        // 12 (E = 192) / 4 (E = 64)
-      uint4 xr[kPer];
-#pragma unroll
-      for (int k = 0; k < kPer; ++k) {
-        const int i = tid + k * kTcWorkers;
-        const int row = i / kUnits, unit = i - row * kUnits;
-        const int pix = sPix[row];
-        xr[k] = make_uint4(0, 0, 0, 0);
-        if (pix >= 0) xr[k] = *reinterpret_cast<const uint4*>(p.x + (long long)pix * p.x_ld + unit * 8);
-      }
+      int* const sPix = sPix2 + 128 * (n_tile & 1);
+      if (n_tile == 0) issue_gather(pair, sPix);             // (later tiles: issued under the previous tile's epilogue)
       // ---- norm1 affine of the windows' images (recomputed only when the image changes) ----
       const bool need_ab = (n_img[0] != cur_img[0]) || (n_img[1] != cur_img[1]);     // uniform
       if (need_ab) {
         constexpr int cpg = kE / 32;
+        const int nset = (n_img[0] == n_img[1]) ? 1 : 2;     // both windows in one image: derive once, store twice
+        float gam[(2 * kE + kTcWorkers - 1) / kTcWorkers], bet[(2 * kE + kTcWorkers - 1) / kTcWorkers];   // this thread's gamma / beta: in flight early
+#pragma unroll
+        for (int q = 0; q < (2 * kE + kTcWorkers - 1) / kTcWorkers; ++q) {
+          const int idx = tid + q * kTcWorkers;
+          const int c = idx % kE;
+          gam[q] = __ldg(p.gamma + c); bet[q] = __ldg(p.beta + c);
+        }
         if (p.gn_gstat) {
           if (tid < 64) {
             const int k = tid >> 5, gg = tid & 31;
-            const float2 mr = ldcg_f2(p.gn_gstat + ((size_t)n_img[k] * 32 + gg) * 2);
+            const float2 mr = ldcg_f2(p.gn_gstat + ((size_t)(k ? n_img[1] : n_img[0]) * 32 + gg) * 2);
             sMR[(k * 32 + gg) * 2] = mr.x; sMR[(k * 32 + gg) * 2 + 1] = mr.y;
           }
         } else {
           const float ns = (float)HW / (float)p.gn_slots;
-          for (int idx = tid; idx < 2 * kE; idx += kTcWorkers) {
+          for (int idx = tid; idx < nset * kE; idx += kTcWorkers) {
             const int k = idx / kE, c = idx - k * kE;
-            const float2 mq = gn_channel_from_pairs(p.gn_part + (size_t)n_img[k] * p.gn_slots * kE * 2 + (size_t)c * 2, p.gn_slots, kE, ns);
+            const float* pc = p.gn_part + (size_t)(k ? n_img[1] : n_img[0]) * p.gn_slots * kE * 2 + (size_t)c * 2;
+            float2 mq;
+            if (p.gn_slots <= 32) {
+              // same arithmetic and order as gn_channel_from_pairs, but every slot's pair is requested before the first use
+              float2 e[32];
+#pragma unroll
+              for (int sl = 0; sl < 32; ++sl) e[sl] = sl < p.gn_slots ? *reinterpret_cast<const float2*>(pc + (size_t)sl * kE * 2) : make_float2(0.f, 0.f);
+              const float pivot = e[0].x;
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int sl = 0; sl < 32; ++sl)
+                if (sl < p.gn_slots) { const float d = e[sl].x - pivot; s1 += d; s2 += fmaf(ns * d, d, e[sl].y); }
+              const float dm = s1 / (float)p.gn_slots;
+              mq = make_float2(pivot + dm, fmaxf(s2 - ns * (float)p.gn_slots * dm * dm, 0.f));
+            } else {
+              mq = gn_channel_from_pairs(pc, p.gn_slots, kE, ns);
+            }
             sCh[(k * kE + c) * 2] = mq.x; sCh[(k * kE + c) * 2 + 1] = mq.y;
           }
           named_bar_sync(1, kTcWorkers);
-          if (tid < 64) {
+          if (tid < 32 * nset) {
             const int k = tid >> 5, gg = tid & 31;
             float chp[2 * cpg];
 #pragma unroll
             for (int j = 0; j < cpg; ++j) { chp[2 * j] = sCh[(k * kE + gg * cpg + j) * 2]; chp[2 * j + 1] = sCh[(k * kE + gg * cpg + j) * 2 + 1]; }
             const float2 mr = gn_group_from_channels(chp, cpg, (float)HW, p.eps);
             sMR[(k * 32 + gg) * 2] = mr.x; sMR[(k * 32 + gg) * 2 + 1] = mr.y;
+            if (nset == 1) { sMR[((32 + gg)) * 2] = mr.x; sMR[((32 + gg)) * 2 + 1] = mr.y; }
           }
         }
         named_bar_sync(1, kTcWorkers);
-        for (int idx = tid; idx < 2 * kE; idx += kTcWorkers) {
+#pragma unroll
+        for (int q = 0; q < (2 * kE + kTcWorkers - 1) / kTcWorkers; ++q) {
+          const int idx = tid + q * kTcWorkers;
+          if (idx >= 2 * kE) break;
           const int k = idx / kE, c = idx - k * kE, gg = c / cpg;
-          const float a = sMR[(k * 32 + gg) * 2 + 1] * __ldg(p.gamma + c);
-          const float b = __ldg(p.beta + c) - sMR[(k * 32 + gg) * 2] * a;
+          const float a = sMR[(k * 32 + gg) * 2 + 1] * gam[q];
+          const float b = bet[q] - sMR[(k * 32 + gg) * 2] * a;
           sAB[(k * kE + c) * 2] = a; sAB[(k * kE + c) * 2 + 1] = b;
         }
         cur_img[0] = n_img[0]; cur_img[1] = n_img[1];
         named_bar_sync(1, kTcWorkers);
       }
-      if (stamp) dbg[1] = clock64() - t_start;
-      // ---- normalise, write the A operand (K-major, 128B swizzle) ----
+      if (stamp) dbgw[1] = clock64() - t_start;
+      // ---- normalise in place: unit gu of rows gr0, gr0 + kRowLanes, ... of each window ----
+      cp_async_wait<0>();
+      if (gact) {
 #pragma unroll
-      for (int k = 0; k < kPer; ++k) {
-        const int i = tid + k * kTcWorkers;
-        const int row = i / kUnits, unit = i - row * kUnits;
-        const float* ab = sAB + ((size_t)(row >> 6) * kE + unit * 8) * 2;
-        uint4 raw = xr[k];
-        __half2* hh = reinterpret_cast<__half2*>(&raw);
+        for (int k = 0; k < 2; ++k) {
+          if ((2 * pair + k) >= p.total_windows) continue;   // (rows of a missing window stay zero)
+          float4 ab[4];                                      // (a, b) of channels 2j, 2j + 1 of this unit, window k
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 c4 = *reinterpret_cast<const float4*>(ab + 4 * j);      // (a, b) of channels 2j, 2j + 1
-          float2 f = __half22float2(hh[j]);
-          f.x = fmaf(f.x, c4.x, c4.y);
-          f.y = fmaf(f.y, c4.z, c4.w);
-          hh[j] = __floats2half2_rn(f.x, f.y);
+          for (int j = 0; j < 4; ++j) ab[j] = *reinterpret_cast<const float4*>(sAB + ((size_t)k * kE + gu * 8) * 2 + 4 * j);
+#pragma unroll
+          for (int it = 0; it < kIt; ++it) {
+            const int lr = gr0 + it * kRowLanes;
+            if (lr < 64) {
+              const int row = k * 64 + lr;
+              uint4* ptr = reinterpret_cast<uint4*>(pXn + (gu >> 3) * 16384 + row * 128 + (((gu & 7) ^ (row & 7)) << 4));
+              uint4 raw = *ptr;
+              __half2* hh = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(hh[j]);
+                f.x = fmaf(f.x, ab[j].x, ab[j].y);
+                f.y = fmaf(f.y, ab[j].z, ab[j].w);
+                hh[j] = __floats2half2_rn(f.x, f.y);
+              }
+              *ptr = raw;
+            }
+          }
         }
-        if (sPix[row] < 0) raw = make_uint4(0, 0, 0, 0);
-        st_shared_v4(sXn + (uint32_t)(unit >> 3) * 16384 + (uint32_t)row * 128 + ((((uint32_t)unit & 7) ^ ((uint32_t)row & 7)) << 4), raw.x, raw.y, raw.z, raw.w);
       }
       fence_proxy_async_smem();
       tc_fence_before();                                     // (this warp's TMEM reads of the previous tile's y are complete)
       named_bar_sync(1, kTcWorkers);                         // the affine scratch (inside the P buffers) is dead from here on
       if (lane == 0) mbar_arrive(xn_full);
-      if (stamp) dbg[2] = clock64() - t_start;
+      if (stamp) dbgw[2] = clock64() - t_start;
 
-      // shifted-window mask: bit b of mbits = key column b has a different region label than this row (reference quirk:
-      // the label depends on the window row and the token COLUMN, see window_attn.cuh)
-      uint32_t mbits = 0;
-      if (p.shift) {
-        const int la = swin_label(wy_[wi], ti & 7, p.H, p.shift);
+      // shifted-window mask (reference quirk: the label depends on the window row and the token COLUMN, see
+      // window_attn.cuh): mval[b] = -100 when key column b carries another region label than this query row
+      float mval[8];
 #pragma unroll
-        for (int b = 0; b < 8; ++b) if (swin_label(wy_[wi], b, p.H, p.shift) != la) mbits |= 1u << b;
+      for (int b = 0; b < 8; ++b) mval[b] = 0.f;
+      if (p.shift) {
+        const int wyw = wi ? wy_[1] : wy_[0];
+        const int la = swin_label(wyw, ti & 7, p.H, p.shift);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) if (swin_label(wyw, b, p.H, p.shift) != la) mval[b] = -100.0f;
       }
 
       for (int g = 0; g < kG; ++g) {
         // ---- drain [Q_g | K_g | V_g] (+ bias, fp16) into the attention operands ----
+        // warps 0-3: Q_g (4 chunks of 16 columns) + V columns [0, 32);  warps 4-7: K_g + V columns [32, 64)
+        const float4* bq4 = reinterpret_cast<const float4*>(p.bqkv + (hf ? kE : 0) + g * 64);
+        const float* bv1 = p.bqkv + 2 * kE + g * 64 + hf * 32;
         mbar_wait(acc_full, n_grp & 1);
         if (n_grp > 0) { mbar_wait(&o_full[0], (n_grp - 1) & 1); mbar_wait(&o_full[1], (n_grp - 1) & 1); }   // last group's MMAs have read Q / K / V^T / P
         tc_fence_after();
-        if (stamp) dbg[3 + g * 6] = clock64() - t_start;
+        if (stamp) dbgw[3 + g * 6] = clock64() - t_start;
         {
-          // warps 0-3: Q_g (4 chunks of 16 columns) + V columns [0, 32);  warps 4-7: K_g + V columns [32, 64)
-          const uint32_t dstQK = (hf ? sK : sQ) + (uint32_t)r * 128;
-          const float* bqk = p.bqkv + (hf ? kE : 0) + g * 64;
-          uint32_t v[4][16];
+          uint32_t v[4][16], vv[2][16];
 #pragma unroll
           for (int c = 0; c < 4; ++c) tmem_ld16(tm_row + (uint32_t)(hf * 64 + c * 16), v[c]);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld_wait16(v[c]);
-          uint32_t vv[2][16];
-#pragma unroll
           for (int c = 0; c < 2; ++c) tmem_ld16(tm_row + (uint32_t)(128 + hf * 32 + c * 16), vv[c]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld_wait16(v[c]);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) tmem_ld_wait16(vv[c]);
+          uint8_t* dstQK = (hf ? pK : pQ) + r * 128;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4 o0, o1;
-            tc_pack16(v[c], bqk + c * 16, o0, o1);
-            st_shared_v4(dstQK + ((((uint32_t)(2 * c)) ^ rsw) << 4), o0.x, o0.y, o0.z, o0.w);
-            st_shared_v4(dstQK + ((((uint32_t)(2 * c + 1)) ^ rsw) << 4), o1.x, o1.y, o1.z, o1.w);
-          }
+            float4 b4[4];
 #pragma unroll
-          for (int c = 0; c < 2; ++c) tmem_ld_wait16(vv[c]);
+            for (int i = 0; i < 4; ++i) b4[i] = __ldg(bq4 + c * 4 + i);
+            tc_pack16(v[c], b4, o0, o1);
+            *reinterpret_cast<uint4*>(dstQK + (((2 * c) ^ rsw) << 4)) = o0;
+            *reinterpret_cast<uint4*>(dstQK + (((2 * c + 1) ^ rsw) << 4)) = o1;
+          }
+          // Q_g / K_g are in place and every TMEM read of the accumulator is complete: the issuer may start S (needs Q, K
+          // of all eight warps) and the next group's QKV GEMM; V^T (needed by PV only) follows, covered by p_full
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(qkv_drained);
+          if (stamp) dbgw[4 + g * 6] = clock64() - t_start;
           // V transposed: element (channel cr, token r) -> token block r / 64, row cr, column r % 64
-          const float* bv = p.bqkv + 2 * kE + g * 64 + hf * 32;
-          const uint32_t vt_tok = sVT + (uint32_t)wi * 8192 + (uint32_t)(r & 7) * 2;
-          const uint32_t tu = (uint32_t)(ti >> 3);
+          uint8_t* vt_tok = pVT + wi * 8192 + (r & 7) * 2;
+          const int tu = ti >> 3;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int cr = hf * 32 + c * 16 + i;
-              const float f = __uint_as_float(vv[c][i]) + __ldg(bv + c * 16 + i);
-              st_shared_u16(vt_tok + (uint32_t)cr * 128 + ((tu ^ ((uint32_t)cr & 7)) << 4), __half_as_ushort(__float2half_rn(f)));
+              const float f = __uint_as_float(vv[c][i]) + __ldg(bv1 + c * 16 + i);
+              *reinterpret_cast<__half*>(vt_tok + cr * 128 + ((tu ^ (cr & 7)) << 4)) = __float2half_rn(f);
             }
           }
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(qkv_drained);
-        if (stamp) dbg[4 + g * 6] = clock64() - t_start;
 
         // ---- softmax of head h = 2 g + hf: this thread owns query row r (token ti of window wi) ----
-        const int h = 2 * g + hf;
+        // bias(i, j) = table[(yi - yj + 7) * 15 + (xi - xj + 7)] = tab_i[-(15 yj + xj)]: a compile-time offset per key j
+        const float* tab_i = sRpb + (2 * g + hf) * 225 + (ti >> 3) * 15 + (ti & 7) + 112;
         float bias[64];
-        {
-          const float4* bp = reinterpret_cast<const float4*>(p.relbias + ((size_t)h * 64 + ti) * 64);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float4 b4 = __ldg(bp + i);
-            bias[4 * i] = b4.x; bias[4 * i + 1] = b4.y; bias[4 * i + 2] = b4.z; bias[4 * i + 3] = b4.w;
-          }
-        }
+        for (int j = 0; j < 64; ++j) bias[j] = tab_i[-(15 * (j >> 3) + (j & 7))];
         const uint32_t tmS = tm_row + (hf ? kTmS1 : kTmS0);
         mbar_wait(&s_full[hf], n_grp & 1);
         tc_fence_after();
-        if (stamp) dbg[5 + g * 6] = clock64() - t_start;
+        if (stamp) dbgw[5 + g * 6] = clock64() - t_start;
         float s[64];
         {
           uint32_t sv[4][16];
@@ -448,139 +570,207 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < 16; ++i) s[16 * c + i] = __uint_as_float(sv[c][i]);
         }
-        float mx = -1e30f;
+        // t = s * scale + bias (+ mask);  p = exp(t - max) = ex2(t * log2e - max * log2e);  four max / sum chains for ILP
+        float mx4[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const float m = ((mbits >> (j & 7)) & 1u) ? -100.0f : 0.f;
-          s[j] = s[j] * p.scale + bias[j] + m;
-          mx = fmaxf(mx, s[j]);
-        }
-        float sum = 0.f;
-        const uint32_t prow = sP + (uint32_t)hf * 16384 + (uint32_t)r * 128;
+        for (int j = 0; j < 64; ++j) { s[j] = fmaf(s[j], p.scale, bias[j]) + mval[j & 7]; mx4[j & 3] = fmaxf(mx4[j & 3], s[j]); }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        const float nmx = -mx * kLog2e;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint8_t* prow = pP + hf * 16384 + r * 128;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          uint32_t q[4];
+          uint4 q;
+          uint32_t* qq = reinterpret_cast<uint32_t*>(&q);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float e0 = __expf(s[8 * u + 2 * i] - mx), e1 = __expf(s[8 * u + 2 * i + 1] - mx);
-            sum += e0; sum += e1;
-            q[i] = pack_h2(e0, e1);
+            const float e0 = tc_ex2(fmaf(s[8 * u + 2 * i], kLog2e, nmx)), e1 = tc_ex2(fmaf(s[8 * u + 2 * i + 1], kLog2e, nmx));
+            sum4[i] += e0 + e1;
+            qq[i] = pack_h2(e0, e1);
           }
-          st_shared_v4(prow + ((((uint32_t)u) ^ rsw) << 4), q[0], q[1], q[2], q[3]);
+          *reinterpret_cast<uint4*>(prow + ((u ^ rsw) << 4)) = q;
         }
-        const float inv = 1.0f / sum;
+        const float inv = 1.0f / ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[hf]);
-        if (stamp) dbg[6 + g * 6] = clock64() - t_start;
+        if (stamp) dbgw[6 + g * 6] = clock64() - t_start;
 
         // ---- O_h = (P V) / rowsum -> fp16, into the projection's A operand (k-block g, 64-byte half hf) ----
         mbar_wait(&o_full[hf], n_grp & 1);
         tc_fence_after();
-        if (stamp) dbg[7 + g * 6] = clock64() - t_start;
+        if (stamp) dbgw[7 + g * 6] = clock64() - t_start;
         {
           uint32_t ov[2][16];
 #pragma unroll
           for (int c = 0; c < 2; ++c) tmem_ld16(tmS + (uint32_t)(32 * wi + 16 * c), ov[c]);
 #pragma unroll
           for (int c = 0; c < 2; ++c) tmem_ld_wait16(ov[c]);
-          const uint32_t orow = sO + (uint32_t)g * 16384 + (uint32_t)r * 128;
+          // O_0 has its own tile; O_g (g >= 1) goes into k-block g of the Xn region, dead once the LAST group's QKV GEMM
+          // has completed (it was issued under this group's softmax at the latest)
+          if (g >= 1) mbar_wait(acc_full, (n_grp + (uint32_t)(kG - 1 - g)) & 1);
+          uint8_t* orow = (g == 0 ? pO : pXn + g * 16384) + r * 128;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            uint32_t q[8];
+            uint4 q0, q1;
+            uint32_t* a0 = reinterpret_cast<uint32_t*>(&q0);
+            uint32_t* a1 = reinterpret_cast<uint32_t*>(&q1);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) q[i] = pack_h2(__uint_as_float(ov[c][2 * i]) * inv, __uint_as_float(ov[c][2 * i + 1]) * inv);
-            st_shared_v4(orow + ((((uint32_t)(4 * hf + 2 * c)) ^ rsw) << 4), q[0], q[1], q[2], q[3]);
-            st_shared_v4(orow + ((((uint32_t)(4 * hf + 2 * c + 1)) ^ rsw) << 4), q[4], q[5], q[6], q[7]);
+            for (int i = 0; i < 4; ++i) {
+              a0[i] = pack_h2(__uint_as_float(ov[c][2 * i]) * inv, __uint_as_float(ov[c][2 * i + 1]) * inv);
+              a1[i] = pack_h2(__uint_as_float(ov[c][8 + 2 * i]) * inv, __uint_as_float(ov[c][8 + 2 * i + 1]) * inv);
+            }
+            *reinterpret_cast<uint4*>(orow + (((4 * hf + 2 * c) ^ rsw) << 4)) = q0;
+            *reinterpret_cast<uint4*>(orow + (((4 * hf + 2 * c + 1) ^ rsw) << 4)) = q1;
           }
         }
-        if (stamp) dbg[8 + g * 6] = clock64() - t_start;
+        if (stamp) dbgw[8 + g * 6] = clock64() - t_start;
         ++n_grp;
       }
+      // the residual (raw x row of this thread, its half of the columns) flies while the projection runs: cp.async into the
+      // Q / K / V^T region — dead once BOTH heads' last PV has completed (this thread waited for its own head's above)
+      mbar_wait(&o_full[hf ^ 1], (n_grp - 1) & 1);
+      constexpr int kHalfCols = kE / 2;                       // columns per worker half
+      constexpr int kCh = kHalfCols / 16;                     // 16-column chunks per thread: 6 / 2
+      uint8_t* const pStage = smem + L::off_q;                // [128 rows][kE] fp16, 16-byte units XOR-swizzled by (row & 7):
+      uint8_t* const pRes = pStage + r * (kE * 2);            // the residual, then (in place) the staged y tile
+      const int mypix = sPix[r];
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_ready);
+      if (mypix >= 0) {
+#pragma unroll
+        for (int u = 0; u < 2 * kCh; ++u)
+          cp_async_16(pRes + (((hf * 2 * kCh + u) ^ rsw) << 4), p.x + (long long)mypix * p.x_ld + hf * kHalfCols + u * 8);
+      }
+      cp_async_commit();
 
-      // ================= epilogue: y = acc + b + x -> fp16 (one rounding), statistics, full-row stores =================
-      const int mypix = sPix[r];
+      // ================= epilogue: y = acc + b + x -> fp16 (one rounding), full-row stores, statistics =================
       const bool want_stats = p.sink[0].part != nullptr;
-      constexpr int kHalfCols = kE / 2;                       // columns per worker half
       mbar_wait(y_full, n_tile & 1);
       tc_fence_after();
-      if (stamp) dbg[24] = clock64() - t_start;
+      cp_async_wait<0>();                                    // this thread's residual units (issued before the o_ready arrival) have landed
+      if (stamp) dbgw[24] = clock64() - t_start;
+      // every MMA of this tile has completed: the Xn tile is free — the next tile's rows start flying now, under the epilogue
+      if (pair + 1 < pair_end) issue_gather(pair + 1, sPix2 + 128 * ((n_tile + 1) & 1));
 #pragma unroll
-      for (int c = 0; c < kHalfCols / 16; ++c) {
-        const int col = hf * kHalfCols + c * 16;
-        uint32_t v[16];
-        tmem_ld16(tm_row + (uint32_t)col, v);
-        uint4 x0 = make_uint4(0, 0, 0, 0), x1 = make_uint4(0, 0, 0, 0);
-        if (mypix >= 0) {
-          const uint4* xp = reinterpret_cast<const uint4*>(p.x + (long long)mypix * p.x_ld + col);
-          x0 = xp[0]; x1 = xp[1];
-        }
-        tmem_ld_wait16(v);
-        float f[16];
+      for (int c0 = 0; c0 < kCh; c0 += 3) {
+        constexpr int kB = kCh < 3 ? kCh : 3;
+        uint32_t v[kB][16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bproj + col) + i);
-          f[4 * i] = __uint_as_float(v[4 * i]) + b4.x; f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
-          f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z; f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
-        }
-        const __half2* h0p = reinterpret_cast<const __half2*>(&x0);
-        const __half2* h1p = reinterpret_cast<const __half2*>(&x1);
-        uint4 o0, o1;
-        __half2* q0 = reinterpret_cast<__half2*>(&o0);
-        __half2* q1 = reinterpret_cast<__half2*>(&o1);
+        for (int c = 0; c < kB; ++c) tmem_ld16(tm_row + (uint32_t)(hf * kHalfCols + (c0 + c) * 16), v[c]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 a0 = __half22float2(h0p[i]), a1 = __half22float2(h1p[i]);
-          q0[i] = __floats2half2_rn(f[2 * i] + a0.x, f[2 * i + 1] + a0.y);
-          q1[i] = __floats2half2_rn(f[8 + 2 * i] + a1.x, f[8 + 2 * i + 1] + a1.y);
+        for (int c = 0; c < kB; ++c) tmem_ld_wait16(v[c]);
+#pragma unroll
+        for (int c = 0; c < kB; ++c) {
+          const int col = hf * kHalfCols + (c0 + c) * 16;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bproj + col) + i);
+            f[4 * i] = __uint_as_float(v[c][4 * i]) + b4.x; f[4 * i + 1] = __uint_as_float(v[c][4 * i + 1]) + b4.y;
+            f[4 * i + 2] = __uint_as_float(v[c][4 * i + 2]) + b4.z; f[4 * i + 3] = __uint_as_float(v[c][4 * i + 3]) + b4.w;
+          }
+          uint4 x0 = make_uint4(0, 0, 0, 0), x1 = make_uint4(0, 0, 0, 0);
+          if (mypix >= 0) {
+            x0 = *reinterpret_cast<const uint4*>(pRes + (((hf * 2 * kCh + 2 * (c0 + c)) ^ rsw) << 4));
+            x1 = *reinterpret_cast<const uint4*>(pRes + (((hf * 2 * kCh + 2 * (c0 + c) + 1) ^ rsw) << 4));
+          }
+          const __half2* h0p = reinterpret_cast<const __half2*>(&x0);
+          const __half2* h1p = reinterpret_cast<const __half2*>(&x1);
+          uint4 o0, o1;
+          __half2* q0 = reinterpret_cast<__half2*>(&o0);
+          __half2* q1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 a0 = __half22float2(h0p[i]), a1 = __half22float2(h1p[i]);
+            q0[i] = __floats2half2_rn(f[2 * i] + a0.x, f[2 * i + 1] + a0.y);
+            q1[i] = __floats2half2_rn(f[8 + 2 * i] + a1.x, f[8 + 2 * i + 1] + a1.y);
+          }
+          // staged over the residual units this thread has just read (the Xn tile already receives the next tile's rows)
+          *reinterpret_cast<uint4*>(pRes + (((hf * 2 * kCh + 2 * (c0 + c)) ^ rsw) << 4)) = o0;
+          *reinterpret_cast<uint4*>(pRes + (((hf * 2 * kCh + 2 * (c0 + c) + 1) ^ rsw) << 4)) = o1;
         }
-        const uint32_t yrow = sXn + (uint32_t)(col >> 6) * 16384 + (uint32_t)r * 128;
-        const uint32_t u0 = (uint32_t)((col & 63) >> 3);
-        st_shared_v4(yrow + ((u0 ^ rsw) << 4), o0.x, o0.y, o0.z, o0.w);
-        st_shared_v4(yrow + (((u0 + 1) ^ rsw) << 4), o1.x, o1.y, o1.z, o1.w);
-        if (want_stats) warp_chunk_stats(o0, o1, lane, sStat + ((size_t)quad * kE + col) * 2);
       }
       tc_fence_before();
       named_bar_sync(1, kTcWorkers);
-      if (stamp) dbg[25] = clock64() - t_start;
-      // full token rows to global
+      if (stamp) dbgw[25] = clock64() - t_start;
+      // full token rows to global: unit gu of rows gr0, gr0 + kRowLanes, ...
+      if (gact) {
 #pragma unroll
-      for (int k = 0; k < kPer; ++k) {
-        const int i = tid + k * kTcWorkers;
-        const int row = i / kUnits, unit = i - row * kUnits;
-        const int pix = sPix[row];
-        if (pix >= 0) {
-          const uint4 val = ld_shared_v4(sXn + (uint32_t)(unit >> 3) * 16384 + (uint32_t)row * 128 + ((((uint32_t)unit & 7) ^ ((uint32_t)row & 7)) << 4));
-          *reinterpret_cast<uint4*>(p.y + (long long)pix * p.y_ld + unit * 8) = val;
-        }
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int it = 0; it < kIt; ++it) {
+            const int lr = gr0 + it * kRowLanes;
+            if (lr < 64) {
+              const int row = k * 64 + lr;
+              const int pix = sPix[row];
+              if (pix >= 0)
+                *reinterpret_cast<uint4*>(p.y + (long long)pix * p.y_ld + gu * 8) =
+                    *reinterpret_cast<const uint4*>(pStage + row * (kE * 2) + ((gu ^ (row & 7)) << 4));
+            }
+          }
       }
       if (want_stats) {
-        // merge the two 32-row quadrants of each window (Chan et al., equal counts) and deliver the window's pairs
-        for (int idx = tid; idx < 2 * kE; idx += kTcWorkers) {
-          const int k = idx / kE, c = idx - k * kE;
-          const int w2 = 2 * pair + k;
-          if (w2 >= p.total_windows) continue;
-          const float m0 = sStat[((size_t)(2 * k) * kE + c) * 2], q0 = sStat[((size_t)(2 * k) * kE + c) * 2 + 1];
-          const float m1 = sStat[((size_t)(2 * k + 1) * kE + c) * 2], q1 = sStat[((size_t)(2 * k + 1) * kE + c) * 2 + 1];
+        // (mean, M2) of the stored values per (window, channel): a second pass over the staged tile.  Thread = (window k,
+        // unit u, sub): 16 rows x 8 channels, the four 16-row parts merged with Chan's formula through shuffles (sub = the
+        // two low lane bits); fixed order.
+        const int su = tid >> 2, sub = tid & 3;
+        const bool sact = su < 2 * kUnits;
+        const int k = sact ? su / kUnits : 0, u = sact ? su % kUnits : 0;
+        float mean8[8], m28[8];
+        {
+          // (sum, sum of squares) over 16 fp16 values per column: q - s^2 / 16 in fp32 is benign for so few values (relative
+          // error ~1e-4 of M2 even for |mean| = 60 std); every later combination is Chan's formula on (mean, M2) pairs
+          float s1[8], s2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int lr = 16 * sub + ((it + 2 * sub) & 15);          // (row & 7 differs between the four subs: fewer bank conflicts)
+            const int row = k * 64 + lr;
+            const uint4 raw = *reinterpret_cast<const uint4*>(pStage + row * (kE * 2) + ((u ^ (row & 7)) << 4));
+            const __half2* hh = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(hh[j]);
+              s1[2 * j] += f.x; s1[2 * j + 1] += f.y;
+              s2[2 * j] = fmaf(f.x, f.x, s2[2 * j]); s2[2 * j + 1] = fmaf(f.y, f.y, s2[2 * j + 1]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            mean8[j] = s1[j] * (1.0f / 16.0f);
+            m28[j] = fmaxf(s2[j] - s1[j] * mean8[j], 0.f);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float m = mean8[j], q = m28[j];
+          float mo = __shfl_xor_sync(0xffffffffu, m, 1), qo = __shfl_xor_sync(0xffffffffu, q, 1);
           float mm, qq;
-          chan_merge_equal(32.f, m0, q0, m1, q1, mm, qq);
+          chan_merge_equal(16.f, (sub & 1) ? mo : m, (sub & 1) ? qo : q, (sub & 1) ? m : mo, (sub & 1) ? q : qo, mm, qq);
+          mo = __shfl_xor_sync(0xffffffffu, mm, 2); qo = __shfl_xor_sync(0xffffffffu, qq, 2);
+          chan_merge_equal(32.f, (sub & 2) ? mo : mm, (sub & 2) ? qo : qq, (sub & 2) ? mm : mo, (sub & 2) ? qq : qo, mean8[j], m28[j]);
+        }
+        const int w2 = 2 * pair + k;
+        if (sact && sub == 0 && w2 < p.total_windows) {
           const int n = w2 / nW, slot = w2 % nW;
 #pragma unroll
           for (int d = 0; d < 2; ++d) {
             const GnSink& sk = p.sink[d];
             if (!sk.part) continue;
-            float* dst = sk.part + (((size_t)n * nW + slot) * sk.cstride + sk.coff + c) * 2;
-            dst[0] = mm; dst[1] = qq;
+            float* dst = sk.part + (((size_t)n * nW + slot) * sk.cstride + sk.coff + u * 8) * 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(mean8[2 * j], m28[2 * j], mean8[2 * j + 1], m28[2 * j + 1]);
           }
         }
       }
       named_bar_sync(1, kTcWorkers);                         // staging / scratch / pixel table are free for the next tile
-      if (stamp) dbg[26] = clock64() - t_start;
+      if (stamp) dbgw[26] = clock64() - t_start;
       ++n_tile;
     }
   }

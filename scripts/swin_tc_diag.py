@@ -109,7 +109,7 @@ def timing(N, H, W, E=192, shift=4, impl="tc", iters=5, timeline=False):
     wq_p, _ = G.pack_weight(wqkv); wp_p, _ = G.pack_weight(wproj)
     y = torch.empty_like(x)
     pout = torch.empty(N, (H // 8) * (W // 8), E, 2, device="cuda")
-    tl = torch.zeros(64, dtype=torch.int64, device="cuda")
+    tl = torch.zeros(128, dtype=torch.int64, device="cuda")
     if timeline:
         _lib.check(G.L.rs_debug_swin_timeline(tl.data_ptr()))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -125,8 +125,9 @@ def timing(N, H, W, E=192, shift=4, impl="tc", iters=5, timeline=False):
     print(f"time impl={impl} N={N} {H}x{W} E={E} shift={shift}: {e0.elapsed_time(e1) * 1e3:.1f} us")
     if timeline:
         t = tl.cpu().tolist()
-        print("   workers [0..26]:", t[:27])
-        print("   mma    [32..47]:", t[32:48])
+        for k in range(2):
+            print(f"   tile {k} workers [0..26]:", t[64 * k:64 * k + 27])
+            print(f"   tile {k} mma    [32..47]:", t[64 * k + 32:64 * k + 48])
 
 
 if __name__ == "__main__":
@@ -138,6 +139,8 @@ if __name__ == "__main__":
         run_case("c", 3, 8, 8, 192, 0, "full")
         run_case("d", 2, 16, 16, 64, 0, "full")
         run_case("e", 1, 64, 64, 192, 4, "full")
+    if what == "ncu":
+        timing(16, 64, 64, shift=4, impl="tc", iters=2)
     if what in ("all", "time"):
         for (H, sh) in ((64, 4), (32, 4), (16, 4), (8, 0)):
             timing(16, H, H, shift=sh, impl="tc", timeline=(H == 64))
