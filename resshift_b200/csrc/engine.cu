@@ -405,8 +405,9 @@ struct Builder {
   // every MLP CTA combining the statistics itself (round 1) and with producer-finalised statistics (profiles/r2_s2:
   // 4.73 vs 4.69 ms per step) — and not faster either way, so it stays OFF (RS_MLP_NORM_FUSE=1 enables it)
   const bool fuse_mlp_norm = env_int("RS_MLP_NORM_FUSE", 0) != 0;
-  // norm1 + qkv + window attention + proj + residual as one kernel per Swin block (RS_SWIN_FUSE=0: four launches)
-  const bool fuse_swin_attn = env_int("RS_SWIN_FUSE", 0) != 0 && !env_is("RS_CONV_IMPL", "simt") && !env_is("RS_ATTN_IMPL", "simt");
+  // norm1 + qkv + window attention + proj + residual as one tcgen05 kernel per Swin block (swin_attn_tc.cuh; RS_SWIN_FUSE=0:
+  // four launches; RS_SWIN_IMPL=mma: the mma.sync version of the fused kernel)
+  const bool fuse_swin_attn = env_int("RS_SWIN_FUSE", 1) != 0 && !env_is("RS_CONV_IMPL", "simt") && !env_is("RS_ATTN_IMPL", "simt");
   const bool fuse_stats = env_int("RS_GN_FUSE", 1) && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt");
   Builder(rs_plan& p) : P(p), E(*p.e), cur(&p.ops) {}
   int list_id() const { return cur == &P.fe_ops ? 0 : 1; }

@@ -61,7 +61,14 @@ struct SwinTcSmem {
   static constexpr int off_bars = off_ring + kSlots * kTcSlotBytes;
   static constexpr int off_pix = off_bars + 256;
   static constexpr int off_rpb = off_pix + 2 * 512;         // relative-position bias, compact: [heads][225] fp32
-  static constexpr int total = off_rpb + (kE / 32) * 225 * 4 + 1024;   // + slack for the 1024-byte alignment of the base
+  static constexpr int off_ab = off_rpb + ((kE / 32) * 225 * 4 + 15) / 16 * 16;   // norm1 affine [2 windows][kE][2] fp32: kept
+                                                            // across the CTA's tiles (recomputed when the image changes)
+  // + slack for aligning the base.  The extern array is declared __align__(1024), which the toolchain honours by rounding
+  // the (empty) static segment up to 1024 bytes — those count against the 227 KB limit — so the pad is 0 in practice;
+  // the kernel traps if it ever exceeds the slack.
+  static constexpr int kSlack = 256;
+  static constexpr int total = off_ab + 2 * kE * 2 * 4 + kSlack;
+  static_assert(total + 1024 <= 227 * 1024, "shared memory budget (dynamic + the 1024-byte static alignment segment)");
 };
 
 #ifdef __CUDACC__
@@ -112,7 +119,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   // (offset arithmetic on the __shared__ array itself: an integer round trip would lose the address space and turn every
   //  plain access below into a generic LD / ST)
-  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  const uint32_t base_pad = (1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u;
+  if (base_pad > (uint32_t)L::kSlack) __trap();
+  uint8_t* smem = tc_smem_raw + base_pad;
   const uint32_t sb = smem_u32(smem);
   const uint32_t sXn = sb + L::off_xn, sO = sb + L::off_o, sQ = sb + L::off_q, sK = sb + L::off_k, sVT = sb + L::off_vt,
                  sP = sb + L::off_p, sRing = sb + L::off_ring;
@@ -130,11 +139,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   int* sPix2 = reinterpret_cast<int*>(smem + L::off_pix);   // [2][128] token -> pixel row, or -1 (this tile's / the next tile's)
   float* sRpb = reinterpret_cast<float*>(smem + L::off_rpb);   // [heads][225]: bias(i, j) = sRpb[h][(yi - yj + 7) * 15 + (xi - xj + 7)]
-  // scratch inside the P buffers (dead at the start and at the end of a tile)
-  float* sAB = reinterpret_cast<float*>(smem + L::off_p);   // [2 windows][kE][2] affine of norm1
-  float* sCh = sAB + 2 * kE * 2;                            // [2][kE][2] per-channel (mean, M2)
+  float* sAB = reinterpret_cast<float*>(smem + L::off_ab);  // [2 windows][kE][2] affine of norm1 (persists across tiles)
+  // scratch inside the P buffers (dead at the start of a tile): only while the affine is being derived
+  float* sCh = reinterpret_cast<float*>(smem + L::off_p);   // [2][kE][2] per-channel (mean, M2)
   float* sMR = sCh + 2 * kE * 2;                            // [2][32][2] group (mean, rstd)
-  float* sStat = reinterpret_cast<float*>(smem + L::off_p); // [4 quads][kE][2] (epilogue)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nWx = p.W >> 3, nWy = p.H >> 3, nW = nWx * nWy;
@@ -362,11 +370,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
     // models/swin_transformer.py:82-97,130-133): it depends on (yi - yj, xi - xj) only.  Keep the 225 distinct values per
     // head in shared memory (5.4 KB) — fetching each warp's 8 KB block of the dense table from L2 for every head of every
     // tile made all SMs hit the same few lines at the same time and cost ~3000 cycles per group (profiles/r2_s19).
-    for (int t = tid; t < (kE / 32) * 225; t += kTcWorkers) {
-      const int h = t / 225, d = t - h * 225;
-      const int dy = d / 15 - 7, dx = d % 15 - 7;
-      const int i = max(dy, 0) * 8 + max(dx, 0), j = max(-dy, 0) * 8 + max(-dx, 0);
-      sRpb[t] = __ldg(p.relbias + ((size_t)h * 64 + i) * 64 + j);
+    constexpr int kRpbPer = ((kE / 32) * 225 + kTcWorkers - 1) / kTcWorkers;
+    float rpb[kRpbPer];                                      // requested now (static data), stored after the first gather is out
+#pragma unroll
+    for (int q = 0; q < kRpbPer; ++q) {
+      const int t = tid + q * kTcWorkers;
+      rpb[q] = 0.f;
+      if (t < (kE / 32) * 225) {
+        const int h = t / 225, d = t - h * 225;
+        const int dy = d / 15 - 7, dx = d % 15 - 7;
+        const int i = max(dy, 0) * 8 + max(dx, 0), j = max(-dy, 0) * 8 + max(-dx, 0);
+        rpb[q] = __ldg(p.relbias + ((size_t)h * 64 + i) * 64 + j);
+      }
     }
     pdl_wait();
 
@@ -383,7 +398,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
         wy_[k] = (w2 % nW) / nWx;
       }
       int* const sPix = sPix2 + 128 * (n_tile & 1);
-      if (n_tile == 0) issue_gather(pair, sPix);             // (later tiles: issued under the previous tile's epilogue)
+      if (n_tile == 0) {
+        issue_gather(pair, sPix);                            // (later tiles: issued under the previous tile's epilogue)
+#pragma unroll
+        for (int q = 0; q < kRpbPer; ++q)
+          if (tid + q * kTcWorkers < (kE / 32) * 225) sRpb[tid + q * kTcWorkers] = rpb[q];   // (visible after the barriers below)
+      }
       // ---- norm1 affine of the windows' images (recomputed only when the image changes) ----
       const bool need_ab = (n_img[0] != cur_img[0]) || (n_img[1] != cur_img[1]);     // uniform
       if (need_ab) {

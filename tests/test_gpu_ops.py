@@ -444,12 +444,16 @@ def test_window_attention(hw, shift, impl):
 
 @pytest.mark.parametrize("impl", ["tc", "mma"])
 @pytest.mark.parametrize("E", [192, 64])
-@pytest.mark.parametrize("case", [(2, 16, 32, 0), (2, 16, 32, 4), (3, 8, 8, 0), (1, 64, 64, 4), (5, 16, 16, 4)])
+@pytest.mark.parametrize("case", [(2, 16, 32, 0), (2, 16, 32, 4), (3, 8, 8, 0), (1, 64, 64, 4), (5, 16, 16, 4), (16, 64, 64, 4)])
 def test_swin_attention_half_fused(case, E, impl, monkeypatch):
     """norm1 + qkv + (shifted-)window attention + proj + residual as ONE kernel against plain torch on the same fp16
     operands, with the intermediate roundings of the unfused path (fp16 n1 / qkv / attention output); also the
-    (mean, M2) pairs of the result per 8x8 window.  reference: models/swin_transformer.py:246-275,114-145."""
+    (mean, M2) pairs of the result per 8x8 window.  reference: models/swin_transformer.py:246-275,114-145.
+    The last case is the benchmark shape: 512 window pairs on 148 persistent CTAs, i.e. several tiles per CTA with the
+    image changing inside a CTA's range (state carried from tile to tile: norm1 affine, weight ring, barrier phases)."""
     from resshift_b200.arch import relative_position_index, shifted_window_mask
+    if case[0] == 16 and E == 64:
+        pytest.skip("the multi-tile case is covered at the model's width")
     monkeypatch.setenv("RS_SWIN_IMPL", impl)       # tc: tcgen05 kernel (swin_attn_tc.cuh); mma: mma.sync kernel (swin_attn_fused.cuh)
     N, H, W, shift = case
     heads = E // 32
