@@ -210,13 +210,16 @@ int rs_op_window_attention(const void* qkv, int N, int H, int W, int heads, int 
 /* fused attention half of a Swin block: y = x + proj(window_attention(qkv(norm1(x)))) (reference
  * models/swin_transformer.py:246-275 with WindowAttention.forward :114-145); x NHWC fp16 [N,H,W,E] (in place when
  * y == x), norm1 statistics as the producers' (mean, M2) pairs gn_part[N][gn_slots][E][2], weights packed fp16;
- * part_out (optional): pairs of y per 8x8 window, [N][(H/8)*(W/8)][E][2].  relbias_dense must be the output of
+ * part_out (optional): pairs of y per 8x8 window, [N][(H/8)*(W/8)][E][2]; gstat_out (optional, tcgen05 kernel only, with
+ * counters [N] zeroed by the caller): the 32 group (mean, rstd) of y per image, finalised by the last CTA to deliver
+ * an image's pairs.  relbias_dense must be the output of
  * rs_op_expand_relpos (relative_position_bias_table gathered by relative_position_index, :82-97,130-133): the tcgen05
  * kernel keeps only its 225 distinct values per head (bias(i, j) depends on (yi - yj, xi - xj) alone).
  * RS_SWIN_IMPL=mma selects the mma.sync kernel (same arithmetic, reads the dense table as given). */
 int rs_op_swin_attn(const void* x, int N, int H, int W, int E, int heads, int shift, const float* gn_part, int gn_slots,
                     const float* gamma, const float* beta, const void* wqkv_packed, const float* bqkv, const float* relbias_dense,
-                    const void* wproj_packed, const float* bproj, void* y, float* part_out, void* stream);
+                    const void* wproj_packed, const float* bproj, void* y, float* part_out, float* gstat_out_or_null,
+                    uint32_t* counters_or_null, void* stream);
 /* fused Swin MLP (reference models/swin_transformer.py:17-33,279): out = residual + fc2(GELU(fc1(x))) */
 int rs_op_mlp(const void* x, int N, int H, int W, int E, int Hd, const void* w1_packed, const float* b1,
               const void* w2_packed, const float* b2, const void* residual, void* out, void* dbg_timeline_or_null,

@@ -834,6 +834,12 @@ bool gn_finalizes(const Op& g) {
 }
 bool gn_producer_finalizes(const Op& g) {
   static const int on = env_int("RS_GN_PRODUCER_FINALIZE", 0);
+  // the tcgen05 Swin attention kernel finalises its own output statistics: its CTAs own runs of consecutive windows, so
+  // every image ends on a different CTA and each CTA arrives once per image (swin_attn_tc.cuh).  Implemented, tested, and
+  // measured slower in the graph (3.98 vs 3.85 ms per step, profiles/r2_s28: the arrival sits on every CTA's tail), so it is
+  // OFF by default (RS_SWIN_FINALIZE=1 enables it); the consumers combine the window pairs
+  static const int swin_fin = env_int("RS_SWIN_FINALIZE", 0);
+  if (g.gn.win_slots) return swin_fin != 0 && swin_attn_uses_tc();
   // (a GroupNorm without a fusable producer runs gn_stats_kernel, whose few CTAs per image arrive themselves)
   return gn_finalizes(g) && (on != 0 || !g.gn.fused);
 }
@@ -1228,7 +1234,8 @@ int rs_plan_forward(rs_plan* p, const float* x, const float* timesteps, const fl
 
 // One forward with a CUDA-event pair around every operator; returns time per kernel family
 // (ms_by_kind[0..3] = conv/linear GEMM, GroupNorm (stats+apply), window attention, upsample) and the
-// algorithmic FLOPs (2*MACs on real, un-padded channels) executed by the conv kernel in that forward.
+// algorithmic FLOPs (2*MACs on real, un-padded channels) executed by the GEMM kernels (conv / linear, fused MLP, fused
+// Swin attention) in that forward.
 int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const float* lq, const float* mask,
                     double* ms_by_kind, double* conv_flops, int32_t* n_conv_launches, void* stream) {
   RS_CHECK(p && p->bound && ms_by_kind && p->vq_which < 0, "bad argument (needs a bound denoiser plan)");
@@ -1245,7 +1252,8 @@ int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const fl
     float ms = 0.f;
     cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]);
     const int kd = prof.kind[i];
-    ms_by_kind[kd == (int)OP_MLP ? 0 : (kd == (int)OP_SWIN_ATTN ? 2 : kd)] += ms;
+    // (the fused Swin attention kernel is a tcgen05 GEMM kernel: qkv + QK^T + PV + proj; it counts with the GEMM family)
+    ms_by_kind[(kd == (int)OP_MLP || kd == (int)OP_SWIN_ATTN) ? 0 : kd] += ms;
   }
   double fl = 0.0; int nc = 0;
   for (const Op& op : p->ops) if (op.kind == OP_MLP) {
@@ -1255,6 +1263,11 @@ int rs_plan_profile(rs_plan* p, const float* x, const float* timesteps, const fl
     const ConvParams& c = op.conv.prm;
     const int cin_real = op.conv.in.tens == p->xin.tens ? p->e->cfg.in_channels + p->e->lq_feat_ch() : op.conv.in.C;
     fl += 2.0 * (double)c.Nimg * c.Hout * c.Wout * c.Cout * (double)c.num_taps * cin_real;
+    ++nc;
+  } else if (op.kind == OP_SWIN_ATTN) {
+    // per token: qkv 2 E 3E + proj 2 E E + (QK^T + PV over the 64 keys of its window) 4 * 64 * E
+    const double M = (double)op.swin.x.N * op.swin.x.H * op.swin.x.W, Ed = (double)op.swin.x.C;
+    fl += M * (8.0 * Ed * Ed + 256.0 * Ed);
     ++nc;
   }
   if (conv_flops) *conv_flops = fl;

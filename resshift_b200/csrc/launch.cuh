@@ -713,6 +713,7 @@ struct SwinAttnDesc {
   long long* dbg = nullptr;
   int grid = 0;
 };
+inline bool swin_attn_uses_tc() { return !env_is("RS_SWIN_IMPL", "mma"); }
 inline bool swin_attn_supported(int E, int heads, int H, int W) {
   return (E == 192 || E == 64) && heads * 32 == E && H % 8 == 0 && W % 8 == 0;
 }
@@ -734,14 +735,18 @@ inline int swin_attn_finalize(SwinAttnDesc& d) {
     int k = 0;
     for (int i = 0; i < 2; ++i) {
       if (!d.sink[i].part) continue;
-      p.sink[k] = d.sink[i]; p.sink[k].gstat = nullptr; p.sink[k].counter = nullptr;     // consumers combine the window pairs
+      p.sink[k] = d.sink[i];
+      if (p.sink[k].expected == 0) p.sink[k].expected = (unsigned)((d.x.H / 8) * (d.x.W / 8) * p.sink[k].cstride);
+      if (p.sink[k].eps == 0.f) p.sink[k].eps = 1e-5f;
       ++k;
     }
   }
   const int pairs = (p.total_windows + 1) / 2;
   d.grid = std::min(pairs, 148);
   // tcgen05 version unless RS_SWIN_IMPL=mma (the mma.sync kernel stays as the tested restatement of the same arithmetic)
-  d.use_tc = !env_is("RS_SWIN_IMPL", "mma") && d.wqkv_ld == E && d.wproj_ld == E;
+  d.use_tc = swin_attn_uses_tc() && d.wqkv_ld == E && d.wproj_ld == E;
+  if (!d.use_tc)                                            // the mma.sync kernel delivers pairs only: consumers combine them
+    for (int k = 0; k < 2; ++k) { p.sink[k].gstat = nullptr; p.sink[k].counter = nullptr; }
   if (d.use_tc) {
     std::memset(&d.tc, 0, sizeof(d.tc));
     d.tc.a = p; d.tc.dbg = d.dbg;

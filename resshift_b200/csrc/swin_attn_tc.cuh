@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
   uint64_t* o_ready = bars + 17;           // 8 worker warps
   uint64_t* y_full = bars + 18;            // commit
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  int* s_flag = reinterpret_cast<int*>(bars + 22);          // [2] "this CTA delivered the image's last pairs" (gn_arrive)
   int* sPix2 = reinterpret_cast<int*>(smem + L::off_pix);   // [2][128] token -> pixel row, or -1 (this tile's / the next tile's)
   float* sRpb = reinterpret_cast<float*>(smem + L::off_rpb);   // [heads][225]: bias(i, j) = sRpb[h][(yi - yj + 7) * 15 + (xi - xj + 7)]
   float* sAB = reinterpret_cast<float*>(smem + L::off_ab);  // [2 windows][kE][2] affine of norm1 (persists across tiles)
@@ -383,6 +384,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
         rpb[q] = __ldg(p.relbias + ((size_t)h * 64 + i) * 64 + j);
       }
     }
+    // Producer-side finalisation of y's statistics (when the sinks carry gstat / counters): this CTA's windows are
+    // consecutive, so the images it touches come in runs — the pairs delivered for the current image are counted and the
+    // CTA arrives ONCE per (sink, image), when it moves on to the next image or after its last tile.  The last arriver of an
+    // image reduces its pairs to the 32 group (mean, rstd) (gn_stats.cuh); different images end on different CTAs.
+    const bool finalize = p.sink[0].part != nullptr && p.sink[0].gstat != nullptr;
+    int pend_img = -1; unsigned int pend_add = 0;            // (identical in every worker thread)
+    auto flush_arrival = [&]() {
+      const GnSink* const sk[2] = {&p.sink[0], (p.sink[1].part && p.sink[1].gstat) ? &p.sink[1] : nullptr};
+      const int im[2] = {pend_img, pend_img};
+      const unsigned int ad[2] = {pend_add, pend_add};
+      gn_arrive<2>(sk, im, ad, nW, 64.0f, tid, kTcWorkers, 1, s_flag);
+      pend_add = 0;
+    };
     pdl_wait();
 
     for (int pair = pair_begin; pair < pair_end; ++pair) {
@@ -517,44 +531,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
         for (int b = 0; b < 8; ++b) if (swin_label(wyw, b, p.H, p.shift) != la) mval[b] = -100.0f;
       }
 
-      for (int g = 0; g < kG; ++g) {
-        // ---- drain [Q_g | K_g | V_g] (+ bias, fp16) into the attention operands ----
-        // warps 0-3: Q_g (4 chunks of 16 columns) + V columns [0, 32);  warps 4-7: K_g + V columns [32, 64)
+      // Per group g:  drain Q_g / K_g (+ bias, fp16) -> S -> V_g^T stores, softmax -> P -> PV -> O_g.  The two MMA round trips
+      // of a group (S, PV) are the serial part: the Q / K drain of group g + 1 (TMEM-bound, ~1000 cycles) is pulled into
+      // the PV wait of group g.  warps 0-3: Q_g (4 chunks of 16 columns) + V columns [0, 32);  warps 4-7: K_g + V [32, 64).
+      uint32_t vv[2][16];                                    // this thread's V values of the group being set up (raw accumulators)
+      auto drain_qk = [&](int g) {
         const float4* bq4 = reinterpret_cast<const float4*>(p.bqkv + (hf ? kE : 0) + g * 64);
-        const float* bv1 = p.bqkv + 2 * kE + g * 64 + hf * 32;
-        mbar_wait(acc_full, n_grp & 1);
-        if (n_grp > 0) { mbar_wait(&o_full[0], (n_grp - 1) & 1); mbar_wait(&o_full[1], (n_grp - 1) & 1); }   // last group's MMAs have read Q / K / V^T / P
-        tc_fence_after();
-        if (stamp) dbgw[3 + g * 6] = clock64() - t_start;
+        uint32_t v[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(tm_row + (uint32_t)(hf * 64 + c * 16), v[c]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tmem_ld16(tm_row + (uint32_t)(128 + hf * 32 + c * 16), vv[c]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_wait16(v[c]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) tmem_ld_wait16(vv[c]);
+        uint8_t* dstQK = (hf ? pK : pQ) + r * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 o0, o1;
+          float4 b4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) b4[i] = __ldg(bq4 + c * 4 + i);
+          tc_pack16(v[c], b4, o0, o1);
+          *reinterpret_cast<uint4*>(dstQK + (((2 * c) ^ rsw) << 4)) = o0;
+          *reinterpret_cast<uint4*>(dstQK + (((2 * c + 1) ^ rsw) << 4)) = o1;
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();                                   // every TMEM read of the accumulator is complete
+      };
+      // group 0: last tile's MMAs have long read Q / K / V^T / P (both o_full of its last group were waited there)
+      mbar_wait(acc_full, n_grp & 1);
+      tc_fence_after();
+      if (stamp) dbgw[3] = clock64() - t_start;
+      drain_qk(0);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qkv_drained);               // S needs Q, K of all eight warps; the next QKV GEMM may start
+      if (stamp) dbgw[4] = clock64() - t_start;
+
+      for (int g = 0; g < kG; ++g) {
+        // ---- V_g^T (needed by PV only; covered by p_full): element (channel cr, token r) -> token block r / 64, row cr,
+        //      column r % 64 ----
         {
-          uint32_t v[4][16], vv[2][16];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld16(tm_row + (uint32_t)(hf * 64 + c * 16), v[c]);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) tmem_ld16(tm_row + (uint32_t)(128 + hf * 32 + c * 16), vv[c]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tmem_ld_wait16(v[c]);
-#pragma unroll
-          for (int c = 0; c < 2; ++c) tmem_ld_wait16(vv[c]);
-          uint8_t* dstQK = (hf ? pK : pQ) + r * 128;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 o0, o1;
-            float4 b4[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) b4[i] = __ldg(bq4 + c * 4 + i);
-            tc_pack16(v[c], b4, o0, o1);
-            *reinterpret_cast<uint4*>(dstQK + (((2 * c) ^ rsw) << 4)) = o0;
-            *reinterpret_cast<uint4*>(dstQK + (((2 * c + 1) ^ rsw) << 4)) = o1;
-          }
-          // Q_g / K_g are in place and every TMEM read of the accumulator is complete: the issuer may start S (needs Q, K
-          // of all eight warps) and the next group's QKV GEMM; V^T (needed by PV only) follows, covered by p_full
-          fence_proxy_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(qkv_drained);
-          if (stamp) dbgw[4 + g * 6] = clock64() - t_start;
-          // V transposed: element (channel cr, token r) -> token block r / 64, row cr, column r % 64
+          const float* bv1 = p.bqkv + 2 * kE + g * 64 + hf * 32;
           uint8_t* vt_tok = pVT + wi * 8192 + (r & 7) * 2;
           const int tu = ti >> 3;
 #pragma unroll
@@ -617,6 +636,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
         if (lane == 0) mbar_arrive(&p_full[hf]);
         if (stamp) dbgw[6 + g * 6] = clock64() - t_start;
 
+        // ---- while PV runs: Q / K of the next group (S of BOTH heads of this group must have read Q / K) ----
+        if (g + 1 < kG) {
+          mbar_wait(acc_full, (n_grp + 1) & 1);
+          mbar_wait(&s_full[hf ^ 1], n_grp & 1);
+          tc_fence_after();
+          drain_qk(g + 1);
+        }
+
         // ---- O_h = (P V) / rowsum -> fp16, into the projection's A operand (k-block g, 64-byte half hf) ----
         mbar_wait(&o_full[hf], n_grp & 1);
         tc_fence_after();
@@ -627,6 +654,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
           for (int c = 0; c < 2; ++c) tmem_ld16(tmS + (uint32_t)(32 * wi + 16 * c), ov[c]);
 #pragma unroll
           for (int c = 0; c < 2; ++c) tmem_ld_wait16(ov[c]);
+          if (g + 1 < kG) {
+            // O_g has left TMEM (S of the next group lands on the same columns) and Q / K of the next group are in place
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(qkv_drained);
+          }
           // O_0 has its own tile; O_g (g >= 1) goes into k-block g of the Xn region, dead once the LAST group's QKV GEMM
           // has completed (it was issued under this group's softmax at the latest)
           if (g >= 1) mbar_wait(acc_full, (n_grp + (uint32_t)(kG - 1 - g)) & 1);
@@ -646,11 +679,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
           }
         }
         if (stamp) dbgw[8 + g * 6] = clock64() - t_start;
+        // the other head's PV has read V^T (and its P rows): the next group's V^T stores / the residual copies may follow
+        mbar_wait(&o_full[hf ^ 1], n_grp & 1);
         ++n_grp;
       }
       // the residual (raw x row of this thread, its half of the columns) flies while the projection runs: cp.async into the
-      // Q / K / V^T region — dead once BOTH heads' last PV has completed (this thread waited for its own head's above)
-      mbar_wait(&o_full[hf ^ 1], (n_grp - 1) & 1);
+      // Q / K / V^T region — dead: BOTH heads' last PV has completed (waited at the end of the group loop)
       constexpr int kHalfCols = kE / 2;                       // columns per worker half
       constexpr int kCh = kHalfCols / 16;                     // 16-column chunks per thread: 6 / 2
       uint8_t* const pStage = smem + L::off_q;                // [128 rows][kE] fp16, 16-byte units XOR-swizzled by (row & 7):
@@ -789,10 +823,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
           }
         }
       }
+      if (finalize) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int w2 = 2 * pair + k;
+          if (w2 >= p.total_windows) continue;
+          const int n = w2 / nW;
+          if (n != pend_img) {
+            if (pend_add) flush_arrival();                   // (the pairs of THIS tile are not counted yet)
+            pend_img = n;
+          }
+          pend_add += (unsigned int)kE;
+        }
+      }
       named_bar_sync(1, kTcWorkers);                         // staging / scratch / pixel table are free for the next tile
       if (stamp) dbgw[26] = clock64() - t_start;
       ++n_tile;
     }
+    if (finalize && pend_add) flush_arrival();
   }
 
   tc_fence_before();

@@ -31,7 +31,7 @@ def run(N, H, W, E=192, shift=4, iters=3):
             e0.record()
         _lib.check(G.L.rs_op_swin_attn(x.data_ptr(), N, H, W, E, heads, shift, part.data_ptr(), slots, gamma.data_ptr(), beta.data_ptr(),
                                        wq_p.data_ptr(), bqkv.data_ptr(), dense.data_ptr(), wp_p.data_ptr(), bproj.data_ptr(),
-                                       y.data_ptr(), pout.data_ptr(), G.stream()))
+                                       y.data_ptr(), pout.data_ptr(), None, None, G.stream()))
     e1.record()
     torch.cuda.synchronize()
     print(f"swin_attn N={N} {H}x{W} E={E}: {e0.elapsed_time(e1) * 1e3:.1f} us")

@@ -71,7 +71,7 @@ def run_case(name, N, H, W, E, shift, mode, impl="tc"):
     pout = torch.full((N, nW, E, 2), float("nan"), dtype=torch.float32, device="cuda")
     _lib.check(G.L.rs_op_swin_attn(x.data_ptr(), N, H, W, E, heads, shift, part.data_ptr(), slots, gamma.data_ptr(), beta.data_ptr(),
                                    wq_p.data_ptr(), bqkv.data_ptr(), dense.data_ptr(), wp_p.data_ptr(), bproj.data_ptr(),
-                                   y.data_ptr(), pout.data_ptr(), G.stream()))
+                                   y.data_ptr(), pout.data_ptr(), None, None, G.stream()))
     torch.cuda.synchronize()
     ref = reference(x, gamma, beta, wqkv, bqkv, table, wproj, bproj, shift)
     d = (y.float() - ref).abs()
@@ -118,7 +118,7 @@ def timing(N, H, W, E=192, shift=4, impl="tc", iters=5, timeline=False):
             e0.record()
         _lib.check(G.L.rs_op_swin_attn(x.data_ptr(), N, H, W, E, heads, shift, part.data_ptr(), slots, gamma.data_ptr(), beta.data_ptr(),
                                        wq_p.data_ptr(), bqkv.data_ptr(), dense.data_ptr(), wp_p.data_ptr(), bproj.data_ptr(),
-                                       y.data_ptr(), pout.data_ptr(), G.stream()))
+                                       y.data_ptr(), pout.data_ptr(), None, None, G.stream()))
     e1.record()
     torch.cuda.synchronize()
     _lib.check(G.L.rs_debug_swin_timeline(None))

@@ -482,13 +482,18 @@ def test_swin_attention_half_fused(case, E, impl, monkeypatch):
     for rep in range(2):
         y = torch.full_like(x, float("nan"))
         pout = torch.full((N, nW, E, 2), float("nan"), dtype=torch.float32, device="cuda")
+        # the tcgen05 kernel also finalises the image's 32 group (mean, rstd) on the last CTA to deliver its pairs
+        gst = torch.full((N, 32, 2), float("nan"), dtype=torch.float32, device="cuda") if impl == "tc" else None
+        cnt = torch.zeros(N, dtype=torch.int32, device="cuda") if impl == "tc" else None
         _lib.check(G.L.rs_op_swin_attn(x.data_ptr(), N, H, W, E, heads, shift, part.data_ptr(), slots, gamma.data_ptr(), beta.data_ptr(),
                                        wq_p.data_ptr(), bqkv.data_ptr(), dense.data_ptr(), wp_p.data_ptr(), bproj.data_ptr(),
-                                       y.data_ptr(), pout.data_ptr(), G.stream()))
+                                       y.data_ptr(), pout.data_ptr(), gst.data_ptr() if gst is not None else None,
+                                       cnt.data_ptr() if cnt is not None else None, G.stream()))
         torch.cuda.synchronize()
-        outs.append((y, pout))
+        outs.append((y, pout, gst))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-    y, pout = outs[0]
+    assert impl != "tc" or torch.equal(outs[0][2], outs[1][2])
+    y, pout, gst = outs[0]
     # ---- reference (fp32 math on fp16-rounded operands, fp16 rounding where the unfused path stores) ----
     xc = x.float().cpu()
     xn = F.group_norm(xc.permute(0, 3, 1, 2), 32, gamma.cpu(), beta.cpu(), eps=1e-5).half().float()           # [N,E,H,W]
@@ -522,6 +527,14 @@ def test_swin_attention_half_fused(case, E, impl, monkeypatch):
     assert not torch.isnan(pout).any()
     assert (pout[..., 0].cpu() - m_ref).abs().max().item() <= 1e-4 * (1 + m_ref.abs().max().item())
     assert ((pout[..., 1].cpu() - q_ref).abs() / (q_ref + 1e-3)).max().item() <= 2e-3
+    if gst is not None:
+        # group statistics of the stored y per image: 32 groups of E / 32 channels over all pixels (biased variance, eps 1e-5)
+        yg = y.float().cpu().permute(0, 3, 1, 2).reshape(N, 32, -1)
+        m_g = yg.mean(dim=2)
+        r_g = (yg.var(dim=2, unbiased=False) + 1e-5).rsqrt()
+        assert not torch.isnan(gst).any()
+        assert (gst[..., 0].cpu() - m_g).abs().max().item() <= 1e-4 * (1 + m_g.abs().max().item())
+        assert ((gst[..., 1].cpu() - r_g).abs() / r_g).max().item() <= 2e-3
 
 
 def test_upsample_and_p_sample():
