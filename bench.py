@@ -499,7 +499,8 @@ def run_gpu(args):
     traffic, tensor_pct, ncu_file = newest_ncu_summary()
     roofline = {
         "kernel": "tcgen05 GEMM kernels: conv_gemm_sm100_kernel<1|2>, conv_gemm_persist_sm100_kernel<1|2> (all conv3x3 / "
-                  "conv1x1 / linear layers) + mlp_fused_sm100_kernel (Swin MLPs)", "bound": "tensor",
+                  "conv1x1 / linear layers) + mlp_fused_sm100_kernel (Swin MLPs) + swin_attn_tc_kernel (norm1 + qkv + window "
+                  "attention + proj of every Swin block)", "bound": "tensor",
         "achieved": conv_tflops, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
         "frac": conv_tflops / peaks["tensor_tflops"],
         # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the GEMM launches of the newest committed
@@ -507,7 +508,7 @@ def run_gpu(args):
         "traffic": traffic if B == BATCH_PER_GPU else None,
         "launches_per_forward": int(nconv.value), "avg_launch_us": pk[0] * 1e3 / max(1, nconv.value),
         "algorithmic_gflop_per_forward": flops.value / 1e9, "peak_source": peaks["source"],
-        "per_forward_ms_by_kernel": {"conv_gemm": pk[0], "groupnorm": pk[1], "window_attn": pk[2], "upsample": pk[3]},
+        "per_forward_ms_by_kernel": {"gemm_family": pk[0], "groupnorm": pk[1], "window_attn_unfused": pk[2], "upsample": pk[3]},
         "traffic_source": f"profiles/{ncu_file}" if ncu_file else None,
         "tensor_pipe_active_pct_ncu": tensor_pct,
         "note": "achieved = algorithmic FLOPs of all GEMM launches / sum of their durations, CUDA events around every "

@@ -106,6 +106,15 @@ __device__ __forceinline__ bool mbar_test_all(uint64_t* bar, uint32_t parity) {
   return __all_sync(0xffffffffu, ok != 0 ? 1 : 0) != 0;
 }
 
+// all worker threads: deliver `add` channel-slots of image `img` to the sinks' arrival counters; the last arriver of an
+// image reduces its pairs to the 32 group (mean, rstd) (gn_stats.cuh)
+__device__ __noinline__ void swin_tc_arrive(const SwinAttnParams& p, int img, unsigned int add, int slots, int tid, int* s_flag) {
+  const GnSink* const sk[2] = {&p.sink[0], (p.sink[1].part && p.sink[1].gstat) ? &p.sink[1] : nullptr};
+  const int im[2] = {img, img};
+  const unsigned int ad[2] = {add, add};
+  gn_arrive<2>(sk, im, ad, slots, 64.0f, tid, kTcWorkers, 1, s_flag);
+}
+
 template <int kE>
 __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __grid_constant__ SwinTcParams prm) {
   using L = SwinTcSmem<kE>;
@@ -391,10 +400,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
     const bool finalize = p.sink[0].part != nullptr && p.sink[0].gstat != nullptr;
     int pend_img = -1; unsigned int pend_add = 0;            // (identical in every worker thread)
     auto flush_arrival = [&]() {
-      const GnSink* const sk[2] = {&p.sink[0], (p.sink[1].part && p.sink[1].gstat) ? &p.sink[1] : nullptr};
-      const int im[2] = {pend_img, pend_img};
-      const unsigned int ad[2] = {pend_add, pend_add};
-      gn_arrive<2>(sk, im, ad, nW, 64.0f, tid, kTcWorkers, 1, s_flag);
+      swin_tc_arrive(p, pend_img, pend_add, nW, tid, s_flag);          // (out of line: rare, and its registers stay out of the tile loop)
       pend_add = 0;
     };
     pdl_wait();
