@@ -1,7 +1,8 @@
 """Two-GPU run of the sampler surface: one process per GPU under NCCL, the reference's ceil(bs / world)
 slicing (sampler.py:273-277), ONE weight broadcast (rank 1 starts from different weights), a final all-gather — all of it
-through resshift_b200.parallel, the same code bench.py --gpus N runs.  The gathered batch must equal, bit for bit, the
-single-GPU run of the whole batch on rank 0 (image shards are independent: nothing inside the loop communicates).
+through resshift_b200.parallel, the same code bench.py --gpus N runs.  Every shard of the gathered batch must equal, bit
+for bit, the single-GPU run of that slice on rank 0 (image shards are independent: nothing inside the loop communicates),
+and the whole-batch run to rounding.
 Skipped on boxes with fewer than two devices (the default round-end box has one)."""
 import os
 
@@ -28,10 +29,10 @@ def _worker(rank, world, port, q):
         s.broadcast_weights(src=0)
         batch = 5                                             # uneven: rank 0 gets 3 images, rank 1 gets 2
         g = torch.Generator(device="cuda").manual_seed(99)
-        y_all = torch.rand(batch, 3, 32, 32, device="cuda", generator=g) * 2 - 1
+        y_all = torch.rand(batch, 3, 64, 64, device="cuda", generator=g) * 2 - 1   # (latent = LQ size: sf 1; 64 = 8 * 2^(levels-1))
         a, b = parallel.shard_range(batch, world, rank)
         s.setup_seed(1234)                                    # same noise stream on every rank ...
-        noise_all = torch.randn(s.base_diffusion.num_timesteps + 1, batch, 3, 32, 32, device="cuda")
+        noise_all = torch.randn(s.base_diffusion.num_timesteps + 1, batch, 3, 64, 64, device="cuda")
 
         def run(y, noise):      # the hot path proper with explicit noise: prior sample + T denoise steps inside librs_b200
             return s.base_diffusion.sample_latent(y, s.model, {"lq": y}, noises=noise).clone()
@@ -39,9 +40,19 @@ def _worker(rank, world, port, q):
         full = s.gather_results(local, batch)
         ok, info = True, ""
         if rank == 0:
+            # every rank's slice re-run on rank 0 AT THE SLICE'S OWN BATCH SIZE must reproduce the gathered shard bit for bit
+            # (same weights after the broadcast, kernels bit-reproducible across GPUs, gather in rank order); the planner
+            # picks other tile shapes / split-K factors for other batch sizes, so the whole-batch run agrees to rounding
+            # only (see test_batch_independence_at_bench_size)
+            ok = full.shape == y_all.shape
+            for rr in range(world):
+                aa, bb = parallel.shard_range(batch, world, rr)
+                again = run(y_all[aa:bb].contiguous(), noise_all[:, aa:bb].contiguous())
+                ok = ok and bool(torch.equal(full[aa:bb], again))
             whole = run(y_all, noise_all)
-            ok = full.shape == whole.shape and bool(torch.equal(full, whole))
-            info = f"max |d| = {(full - whole).abs().max().item():.3e}"
+            dmax = (full - whole).abs().max().item()
+            ok = ok and dmax <= 2e-2
+            info = f"shards bit-identical: {ok}; vs the whole-batch plan max |d| = {dmax:.3e}"
         q.put((rank, ok, info))
     except Exception as exc:                                  # noqa: BLE001 — report instead of hanging the parent
         import traceback
