@@ -408,6 +408,13 @@ struct Builder {
   // norm1 + qkv + window attention + proj + residual as one tcgen05 kernel per Swin block (swin_attn_tc.cuh; RS_SWIN_FUSE=0:
   // four launches; RS_SWIN_IMPL=mma: the mma.sync version of the fused kernel)
   const bool fuse_swin_attn = env_int("RS_SWIN_FUSE", 1) != 0 && !env_is("RS_CONV_IMPL", "simt") && !env_is("RS_ATTN_IMPL", "simt");
+  // measured in the graph (profiles/r2_s33_min_pairs.log; ms per denoise step, fused from N pairs up):
+  //   batch 16: all levels 3.876, >= 9: 3.834, >= 33 (64x64 + 32x32): 3.809, >= 129 (64x64 only): 3.846, none: 3.902
+  //   batch  8: all 2.920, >= 33 (64x64 + 32x32 with 64 pairs): 2.826, >= 129 (64x64 only): 2.812, none: 2.877
+  //   batch  1: all 2.252, none 2.097 (64x64 = 32 pairs)
+  // i.e. the fused kernel wins where its persistent CTAs cover most of the machine (>= ~100 window pairs) and loses where a
+  // level is one 29-us tile on a few SMs against four small launches whose prologues overlap.
+  const int fuse_swin_min_pairs = env_int("RS_SWIN_FUSE_MIN_PAIRS", 96);
   const bool fuse_stats = env_int("RS_GN_FUSE", 1) && !env_is("RS_CONV_EPI", "direct") && !env_is("RS_CONV_IMPL", "simt");
   Builder(rs_plan& p) : P(p), E(*p.e), cur(&p.ops) {}
   int list_id() const { return cur == &P.fe_ops ? 0 : 1; }
@@ -559,7 +566,11 @@ struct Builder {
     for (int i = 0; i < c.swin_depth; ++i) {
       const std::string b = p + ".blocks." + std::to_string(i);
       // x = x + proj(attn(qkv(norm1(x)))): one kernel (swin_attn_fused.cuh), or the four-launch sequence
-      if (!(fuse_swin_attn && swin_attn_supported(Ed, c.swin_heads, x.H, x.W) && swin_attn(e, b, c.swin_heads, (i % 2) ? shift_odd : 0))) {
+      // (a level with few window pairs is one long serial tile per CTA on a handful of SMs: below fuse_swin_min_pairs the
+      //  four small launches, whose prologues overlap through PDL, are faster in the graph)
+      const int win_pairs = (x.N * (x.H / 8) * (x.W / 8) + 1) / 2;
+      if (!(fuse_swin_attn && win_pairs >= fuse_swin_min_pairs && swin_attn_supported(Ed, c.swin_heads, x.H, x.W) &&
+            swin_attn(e, b, c.swin_heads, (i % 2) ? shift_odd : 0))) {
         View n1 = P.make_view(x.N, x.H, x.W, Ed);
         gn(e, b + ".norm1", n1, 0, -1);
         View qkv = P.make_view(x.N, x.H, x.W, 3 * Ed);
