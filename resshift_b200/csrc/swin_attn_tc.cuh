@@ -403,6 +403,82 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
       swin_tc_arrive(p, pend_img, pend_add, nW, tid, s_flag);          // (out of line: rare, and its registers stay out of the tile loop)
       pend_add = 0;
     };
+    // Statistics of a finished tile: (mean, M2) per (window, channel) from the staged y tile (+ arrival bookkeeping).  For
+    // all but a CTA's last tile this runs in the NEXT tile, while the workers would otherwise wait for its first QKV GEMM —
+    // the staged tile (Q / K / V^T region) is overwritten only by that tile's first drain.
+    const bool want_stats = p.sink[0].part != nullptr;
+    uint8_t* const pStage = smem + L::off_q;                  // [128 rows][kE] fp16, 16-byte units XOR-swizzled by (row & 7)
+    auto stats_pass = [&](int pr) {
+      if (want_stats) {
+        // (mean, M2) of the stored values per (window, channel): a second pass over the staged tile.  Thread = (window k,
+        // unit u, sub): 16 rows x 8 channels, the four 16-row parts merged with Chan's formula through shuffles (sub = the
+        // two low lane bits); fixed order.
+        const int su = tid >> 2, sub = tid & 3;
+        const bool sact = su < 2 * kUnits;
+        const int k = sact ? su / kUnits : 0, u = sact ? su % kUnits : 0;
+        float mean8[8], m28[8];
+        {
+          // (sum, sum of squares) over 16 fp16 values per column: q - s^2 / 16 in fp32 is benign for so few values (relative
+          // error ~1e-4 of M2 even for |mean| = 60 std); every later combination is Chan's formula on (mean, M2) pairs
+          float s1[8], s2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+#pragma unroll
+          for (int it = 0; it < 16; ++it) {
+            const int lr = 16 * sub + ((it + 2 * sub) & 15);          // (row & 7 differs between the four subs: fewer bank conflicts)
+            const int row = k * 64 + lr;
+            const uint4 raw = *reinterpret_cast<const uint4*>(pStage + row * (kE * 2) + ((u ^ (row & 7)) << 4));
+            const __half2* hh = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(hh[j]);
+              s1[2 * j] += f.x; s1[2 * j + 1] += f.y;
+              s2[2 * j] = fmaf(f.x, f.x, s2[2 * j]); s2[2 * j + 1] = fmaf(f.y, f.y, s2[2 * j + 1]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            mean8[j] = s1[j] * (1.0f / 16.0f);
+            m28[j] = fmaxf(s2[j] - s1[j] * mean8[j], 0.f);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float m = mean8[j], q = m28[j];
+          float mo = __shfl_xor_sync(0xffffffffu, m, 1), qo = __shfl_xor_sync(0xffffffffu, q, 1);
+          float mm, qq;
+          chan_merge_equal(16.f, (sub & 1) ? mo : m, (sub & 1) ? qo : q, (sub & 1) ? m : mo, (sub & 1) ? q : qo, mm, qq);
+          mo = __shfl_xor_sync(0xffffffffu, mm, 2); qo = __shfl_xor_sync(0xffffffffu, qq, 2);
+          chan_merge_equal(32.f, (sub & 2) ? mo : mm, (sub & 2) ? qo : qq, (sub & 2) ? mm : mo, (sub & 2) ? qq : qo, mean8[j], m28[j]);
+        }
+        const int w2 = 2 * pr + k;
+        if (sact && sub == 0 && w2 < p.total_windows) {
+          const int n = w2 / nW, slot = w2 % nW;
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            const GnSink& sk = p.sink[d];
+            if (!sk.part) continue;
+            float* dst = sk.part + (((size_t)n * nW + slot) * sk.cstride + sk.coff + u * 8) * 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(mean8[2 * j], m28[2 * j], mean8[2 * j + 1], m28[2 * j + 1]);
+          }
+        }
+      }
+      if (finalize) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int w2 = 2 * pr + k;
+          if (w2 >= p.total_windows) continue;
+          const int n = w2 / nW;
+          if (n != pend_img) {
+            if (pend_add) flush_arrival();                   // (the pairs of THIS tile are not counted yet)
+            pend_img = n;
+          }
+          pend_add += (unsigned int)kE;
+        }
+      }
+    };
     pdl_wait();
 
     for (int pair = pair_begin; pair < pair_end; ++pair) {
@@ -566,6 +642,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
         fence_proxy_async_smem();
         tc_fence_before();                                   // every TMEM read of the accumulator is complete
       };
+      if (n_tile > 0) {                                      // the previous tile's statistics, while QKV_0 of this one runs
+        stats_pass(pair - 1);
+        named_bar_sync(1, kTcWorkers);                       // (every thread has read the staged tile before the first drain writes Q / K)
+      }
       // group 0: last tile's MMAs have long read Q / K / V^T / P (both o_full of its last group were waited there)
       mbar_wait(acc_full, n_grp & 1);
       tc_fence_after();
@@ -693,7 +773,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
       // Q / K / V^T region — dead: BOTH heads' last PV has completed (waited at the end of the group loop)
       constexpr int kHalfCols = kE / 2;                       // columns per worker half
       constexpr int kCh = kHalfCols / 16;                     // 16-column chunks per thread: 6 / 2
-      uint8_t* const pStage = smem + L::off_q;                // [128 rows][kE] fp16, 16-byte units XOR-swizzled by (row & 7):
       uint8_t* const pRes = pStage + r * (kE * 2);            // the residual, then (in place) the staged y tile
       const int mypix = sPix[r];
       fence_proxy_async_smem();
@@ -708,7 +787,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
       cp_async_commit();
 
       // ================= epilogue: y = acc + b + x -> fp16 (one rounding), full-row stores, statistics =================
-      const bool want_stats = p.sink[0].part != nullptr;
       mbar_wait(y_full, n_tile & 1);
       tc_fence_after();
       cp_async_wait<0>();                                    // this thread's residual units (issued before the o_ready arrival) have landed
@@ -773,75 +851,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
             }
           }
       }
-      if (want_stats) {
-        // (mean, M2) of the stored values per (window, channel): a second pass over the staged tile.  Thread = (window k,
-        // unit u, sub): 16 rows x 8 channels, the four 16-row parts merged with Chan's formula through shuffles (sub = the
-        // two low lane bits); fixed order.
-        const int su = tid >> 2, sub = tid & 3;
-        const bool sact = su < 2 * kUnits;
-        const int k = sact ? su / kUnits : 0, u = sact ? su % kUnits : 0;
-        float mean8[8], m28[8];
-        {
-          // (sum, sum of squares) over 16 fp16 values per column: q - s^2 / 16 in fp32 is benign for so few values (relative
-          // error ~1e-4 of M2 even for |mean| = 60 std); every later combination is Chan's formula on (mean, M2) pairs
-          float s1[8], s2[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-#pragma unroll
-          for (int it = 0; it < 16; ++it) {
-            const int lr = 16 * sub + ((it + 2 * sub) & 15);          // (row & 7 differs between the four subs: fewer bank conflicts)
-            const int row = k * 64 + lr;
-            const uint4 raw = *reinterpret_cast<const uint4*>(pStage + row * (kE * 2) + ((u ^ (row & 7)) << 4));
-            const __half2* hh = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(hh[j]);
-              s1[2 * j] += f.x; s1[2 * j + 1] += f.y;
-              s2[2 * j] = fmaf(f.x, f.x, s2[2 * j]); s2[2 * j + 1] = fmaf(f.y, f.y, s2[2 * j + 1]);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            mean8[j] = s1[j] * (1.0f / 16.0f);
-            m28[j] = fmaxf(s2[j] - s1[j] * mean8[j], 0.f);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float m = mean8[j], q = m28[j];
-          float mo = __shfl_xor_sync(0xffffffffu, m, 1), qo = __shfl_xor_sync(0xffffffffu, q, 1);
-          float mm, qq;
-          chan_merge_equal(16.f, (sub & 1) ? mo : m, (sub & 1) ? qo : q, (sub & 1) ? m : mo, (sub & 1) ? q : qo, mm, qq);
-          mo = __shfl_xor_sync(0xffffffffu, mm, 2); qo = __shfl_xor_sync(0xffffffffu, qq, 2);
-          chan_merge_equal(32.f, (sub & 2) ? mo : mm, (sub & 2) ? qo : qq, (sub & 2) ? mm : mo, (sub & 2) ? qq : qo, mean8[j], m28[j]);
-        }
-        const int w2 = 2 * pair + k;
-        if (sact && sub == 0 && w2 < p.total_windows) {
-          const int n = w2 / nW, slot = w2 % nW;
-#pragma unroll
-          for (int d = 0; d < 2; ++d) {
-            const GnSink& sk = p.sink[d];
-            if (!sk.part) continue;
-            float* dst = sk.part + (((size_t)n * nW + slot) * sk.cstride + sk.coff + u * 8) * 2;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(mean8[2 * j], m28[2 * j], mean8[2 * j + 1], m28[2 * j + 1]);
-          }
-        }
-      }
-      if (finalize) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int w2 = 2 * pair + k;
-          if (w2 >= p.total_windows) continue;
-          const int n = w2 / nW;
-          if (n != pend_img) {
-            if (pend_add) flush_arrival();                   // (the pairs of THIS tile are not counted yet)
-            pend_img = n;
-          }
-          pend_add += (unsigned int)kE;
-        }
-      }
+      if (pair + 1 == pair_end) stats_pass(pair);            // (earlier tiles: under the next tile's first QKV GEMM)
       named_bar_sync(1, kTcWorkers);                         // staging / scratch / pixel table are free for the next tile
       if (stamp) dbgw[26] = clock64() - t_start;
       ++n_tile;
