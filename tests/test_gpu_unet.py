@@ -99,6 +99,36 @@ def test_norm2_fused_into_mlp_is_bit_identical_to_separate_groupnorm():
     assert not torch.isnan(outs[0][0]).any() and torch.equal(outs[0][0], outs[1][0])
 
 
+def test_fused_swin_attention_plan_matches_four_launch_plan(monkeypatch):
+    """The tcgen05 Swin attention kernel (norm1 + qkv + window attention + proj + residual in one launch) against the
+    four-launch form of the same half, at plan level and WITH workspace reuse: forced on every level
+    (RS_SWIN_FUSE_MIN_PAIRS=1: 18 blocks x 3 launches fewer) vs off.  Same roundings, different summation orders: the
+    outputs agree to rounding; the fused plan is bit-reproducible and right against the oracle.  Batch 3 puts several
+    images and an odd window count (8x8 level: 3 windows) into one CTA's range."""
+    from oracle import unet_oracle as uo
+    outs = {}
+    for thr in ("1", "1000000"):
+        monkeypatch.setenv("RS_SWIN_FUSE_MIN_PAIRS", thr)
+        ucfg, _, m = _model("realsr")
+        g = torch.Generator(device="cuda").manual_seed(11)
+        x = torch.randn(3, 3, 64, 64, device="cuda", generator=g)
+        lq = torch.rand(3, 3, 64, 64, device="cuda", generator=g) * 2 - 1
+        t = torch.tensor([1, 8, 14], device="cuda")
+        a = m(x, t, lq=lq).clone()
+        b = m(x, t, lq=lq).clone()
+        assert torch.equal(a, b) and not torch.isnan(a).any()
+        outs[thr] = (a, m.num_launches(3, 64, 64))
+        del m
+    assert outs["1"][1] == outs["1000000"][1] - 54, (outs["1"][1], outs["1000000"][1])
+    d = (outs["1"][0] - outs["1000000"][0]).abs()
+    print(f"[property] fused vs four-launch Swin attention: max|d|={d.max().item():.3e} mean|d|={d.mean().item():.3e}")
+    assert d.max().item() <= 1e-2 and d.mean().item() <= 1.5e-3
+    sd = random_state_dict(ucfg, 0)
+    ref = uo.unet_forward(sd, ucfg, x.cpu(), t.cpu(), lq=lq.cpu())
+    mx, mn = _report("forward realsr, fused Swin attention on every level", outs["1"][0], ref)
+    assert mx <= FWD_MAX and mn <= FWD_MEAN
+
+
 def test_forward_vs_oracle_fresh_inputs():
     """Oracle on new seeded inputs (not in the goldens), batch 3 with distinct timesteps."""
     from oracle import unet_oracle as uo
