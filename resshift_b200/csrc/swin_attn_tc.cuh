@@ -8,20 +8,30 @@
 // swin_attn_fused_kernel (fp16 n1, fp16 q / k / v with bias, softmax in fp32, un-normalised fp16 P, fp16 O, one final
 // rounding of y) — but every GEMM runs on tcgen05 with the accumulators in TMEM:
 //
-//   * a CTA owns TWO 8x8 windows = 128 token rows = one UMMA M.  The rows are gathered with plain 16-byte loads (cyclic
-//     shift and window partition are address arithmetic), normalised in registers and written into shared memory
-//     directly in the K-major 128B-swizzled operand layout (what a TMA load would have produced);
+//   * a persistent CTA owns a run of consecutive window PAIRS; a tile = TWO 8x8 windows = 128 token rows = one UMMA M.  The
+//     rows are gathered with cp.async straight into their K-major 128B-swizzled operand positions (cyclic shift and window
+//     partition are address arithmetic; the next tile's rows already fly under this tile's epilogue), normalised in place
+//     with the per-image affine of norm1 (kept across tiles, recomputed when the image changes) and fenced to the async
+//     proxy: exactly what a TMA load of a normalised tensor would have produced;
 //   * the heads are walked in GROUPS of two (64 channels): [Q_g | K_g | V_g] = Xn . W_g^T is one N = 192 accumulator
-//     (weight rows stream through a TMA ring), drained to shared memory as fp16 operands — Q_g / K_g row-major (K-major
-//     A / B operands of QK^T), V_g TRANSPOSED (the K-major B operand of PV wants [head_dim][token]);
+//     (weight tiles stream through a three-slot TMA ring: a whole group in flight), drained to shared memory as fp16
+//     operands — Q_g / K_g row-major (K-major A / B operands of QK^T), V_g TRANSPOSED (the K-major B operand of PV wants
+//     [head_dim][token]);
 //   * per head: S = Q_h K_h^T as two N = 64 MMAs (the keys of window 0, the keys of window 1): all 128 rows are multiplied
 //     against each window's keys and each row simply reads the 64 columns of ITS window — block-diagonal attention
-//     without M = 64 instructions.  Softmax: one thread per query row (no shuffles), P written as the next A operand.
-//     O = P V the same way (two N = 32 MMAs into the TMEM columns S just vacated), scaled by 1 / rowsum and written into
-//     the A operand of the projection;
-//   * while the 128 threads of a head do softmax the tensor pipe already runs the NEXT group's QKV GEMM;
-//   * y = O W_proj^T + b + x: N = E accumulator, + raw x re-read from L2, one rounding, staged in shared memory, written as
-//     full token rows; (mean, M2) per (window, channel) for the norm2 that follows.
+//     without M = 64 instructions.  Softmax: one thread per query row (no shuffles), bias from a 225-entry table per head
+//     in shared memory, P written as the next A operand.  O = P V the same way (two N = 32 MMAs into the TMEM columns S
+//     just vacated), scaled by 1 / rowsum and written into the A operand of the projection (O_0 in its own tile, the
+//     later groups' O into the by then dead Xn tile);
+//   * pipelining inside a tile: the next group's QKV GEMM runs under this group's softmax, its Q / K drain under this
+//     group's PV round trip, the projection's first k-blocks under the last group's softmax;
+//   * y = O W_proj^T + b + x: N = E accumulator, + raw x (cp.async into the dead Q / K / V^T region while the projection
+//     runs), one rounding, staged in place, written as full token rows; (mean, M2) per (window, channel) for the norm2
+//     that follows — for all but a CTA's last tile computed while the next tile waits for its first GEMM.
+//
+// TMEM columns: [0, 192) the group's QKV accumulator, later y; [192, 320) and [320, 448) S of the two heads (O on top).
+// What bounds it: TMEM -> register reads at ~64 B/clk per SM (678 KB per tile) and the serial MMA
+// round trips of a tile; levels with fewer than ~100 window pairs keep the four-launch form (engine.cu).
 //
 // Warp roles: warps 0-7 workers (warp w owns TMEM lane quadrant w % 4 = token rows [32 (w % 4), +32); warps 0-3 take
 // the first head of a group, warps 4-7 the second), warp 8 TMA producer (weights), warp 9 TMEM allocation + MMA issue.
