@@ -279,8 +279,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
         // the next group's QKV GEMM runs under this group's softmax; PV_j goes out as soon as P_j is written — whichever
         // of the two is ready first (a k-block waiting for its weight tile must not hold back a finished head)
         int kb_next = (g + 1 < kG) ? 0 : kKB;
-        // last group: the projection's k-blocks 0 .. kKB-2 (O of the earlier groups, complete and fenced before this group's
-        // drain arrived) go out under the softmax as well; only the last one waits for O of this group
+        // last group: the projection's k-blocks 0 .. kKB-2 go out early as well; only the last one waits for O of this group.
+        // O of the earlier groups is written AFTER the worker's arrival on qkv_drained (the arrival only says "Q / K in place,
+        // O has left TMEM"); what publishes those stores is the worker's next fence + arrival — p_full of this group.  So
+        // the early k-blocks follow both PVs of this group (found by compute-sanitizer: results changed from run to run
+        // when the issuer got ahead of the O_1 stores)
         int pj_next = 0;
         const int pj_early = (g + 1 < kG) ? 0 : kKB - 1;
         uint32_t pv_done = 0;
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) swin_attn_tc_kernel(const __gri
             ++kb_next;
             progressed = true;
           }
-          if (pj_next < pj_early && mbar_test_all(&w_full[slot], ph)) {
+          if (pj_next < pj_early && pv_done == 3u && mbar_test_all(&w_full[slot], ph)) {
             tc_fence_after();
             issue_kb(pj_next == 0 ? sO : sXn + (uint32_t)pj_next * 16384, pj_next, idesc_proj, y_full);
             ++pj_next;
